@@ -1,0 +1,654 @@
+// capi.cu — host side of the C ABI declared in include/orz_b200.h.
+//
+// Owns device memory (one arena per batch), drives the kernels, mirrors the reference's stream
+// driver (lib.rs:58-129) and operator interface (lz.rs:75-95, 353-366).  No CPU codec lives here:
+// if CUDA is unavailable every entry point fails with ORZ_ECUDA.
+#include "../../include/orz_b200.h"
+#include "orz_dev.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace orz {
+void launch_parse(EncStream *, int, cudaStream_t);
+void launch_emit(EncStream *, int, cudaStream_t);
+void launch_enc_begin(EncStream *, int, cudaStream_t);
+void launch_enc_forward(EncStream *, uint32_t, cudaStream_t);
+void launch_decode(DecStream *, int, cudaStream_t);
+void launch_dec_forward(DecStream *, uint32_t, cudaStream_t);
+} // namespace orz
+
+using namespace orz;
+
+#define CU_TRY(expr)                                                                                        \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) {                                                                            \
+            if (getenv("ORZ_B200_DEBUG")) fprintf(stderr, "orz_b200: %s failed: %s\n", #expr, cudaGetErrorString(e_)); \
+            return e_ == cudaErrorMemoryAllocation ? ORZ_ENOMEM : ORZ_ECUDA;                                 \
+        }                                                                                                   \
+    } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// timing: CUDA events around every launch, on the launching stream
+// ------------------------------------------------------------------------------------------------
+struct KernelTimer {
+    struct Rec {
+        cudaEvent_t a, b;
+        int cls;
+    };
+    std::vector<Rec> pool;
+    size_t used = 0;
+    float ms[4] = {0, 0, 0, 0};
+    int launches[4] = {0, 0, 0, 0};
+    void reset() {
+        used = 0;
+        for (int i = 0; i < 4; i++) ms[i] = 0, launches[i] = 0;
+    }
+    int begin(int cls, cudaStream_t st) {
+        if (used == pool.size()) {
+            Rec r;
+            cudaEventCreate(&r.a);
+            cudaEventCreate(&r.b);
+            r.cls = cls;
+            pool.push_back(r);
+        }
+        pool[used].cls = cls;
+        cudaEventRecord(pool[used].a, st);
+        return (int)used++;
+    }
+    void end(int id, cudaStream_t st) { cudaEventRecord(pool[id].b, st); }
+    void collect() { // after a stream synchronize
+        for (size_t i = 0; i < used; i++) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, pool[i].a, pool[i].b) == cudaSuccess) {
+                ms[pool[i].cls] += t;
+                launches[pool[i].cls]++;
+            }
+        }
+    }
+    ~KernelTimer() {
+        for (auto &r : pool) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// batch object
+// ------------------------------------------------------------------------------------------------
+struct orz_batch {
+    int device = 0;
+    int mode = 0; // 0 encode, 1 decode
+    int n = 0;
+    orz_lzcfg cfg{};
+    cudaStream_t st = nullptr;
+    uint8_t *arena = nullptr;
+    size_t arena_size = 0;
+    // state region inside the arena that must be reset before each run: [state_off, state_off+state_size)
+    std::vector<EncStream> enc;  // host mirrors (templates)
+    std::vector<DecStream> dec;
+    EncStream *d_enc = nullptr;
+    DecStream *d_dec = nullptr;
+    std::vector<uint8_t *> d_in, d_out; // per-stream device buffers
+    std::vector<size_t> in_cap, in_len, out_cap;
+    std::vector<uint8_t *> zero_lo;     // per-stream [zero_lo, zero_hi) zero-filled before each run
+    std::vector<uint8_t *> zero_hi;
+    std::vector<int16_t *> heads;       // per-stream heads (0xff filled)
+    std::vector<int32_t> status;
+    std::vector<uint64_t> result_len;
+    int32_t *h_status_pinned = nullptr;
+    bool chunk_mode = false; // operator interface: host drives chunks
+    KernelTimer timer;
+    bool ran = false;
+};
+
+static int check_device(int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ORZ_ECUDA;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return ORZ_ECUDA;
+    if (p.major < 10) return ORZ_ECUDA; // the kernels are built for sm_100a only
+    return ORZ_OK;
+}
+
+extern "C" int orz_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    int ok = 0;
+    for (int i = 0; i < count; i++)
+        if (check_device(i) == ORZ_OK) ok++;
+    return ok;
+}
+
+extern "C" const char *orz_strerror(int code) {
+    switch (code) {
+    case ORZ_OK: return "ok";
+    case ORZ_EINVAL: return "invalid data";
+    case ORZ_ENOSPC: return "output buffer too small";
+    case ORZ_EEOF: return "unexpected end of file";
+    case ORZ_ENOMEM: return "out of memory";
+    case ORZ_ECUDA: return "CUDA device/kernel unavailable (no CPU fallback)";
+    case ORZ_EARG: return "invalid argument";
+    default: return "unknown error";
+    }
+}
+
+extern "C" int orz_level_cfg(int level, orz_lzcfg *cfg) { // main.rs:97-102
+    if (!cfg) return ORZ_EARG;
+    switch (level) {
+    case 0: *cfg = {5, 3, 2}; return ORZ_OK;
+    case 1: *cfg = {15, 9, 6}; return ORZ_OK;
+    case 2: *cfg = {45, 27, 18}; return ORZ_OK;
+    default: return ORZ_EARG;
+    }
+}
+
+extern "C" size_t orz_encode_bound(size_t n) { return n + n / 2 + (n / 65536 + 2) * 4096 + 65536; }
+
+struct ArenaPlan {
+    size_t off = 0;
+    size_t take(size_t bytes, size_t align = 256) {
+        off = align_up(off, align);
+        size_t r = off;
+        off += bytes;
+        return r;
+    }
+};
+
+static void batch_destroy(orz_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->st) cudaStreamSynchronize(b->st);
+    if (b->arena) cudaFree(b->arena);
+    if (b->h_status_pinned) cudaFreeHost(b->h_status_pinned);
+    if (b->st) cudaStreamDestroy(b->st);
+    delete b;
+}
+
+// full_window: allocate the whole 32 MiB window even for short inputs (operator interface)
+static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n, const size_t *in_len, const size_t *out_cap,
+                               bool chunk_mode, int *err) {
+    *err = ORZ_OK;
+    if (n <= 0 || (mode == 0 && !cfg)) {
+        *err = ORZ_EARG;
+        return nullptr;
+    }
+    if ((*err = check_device(device)) != ORZ_OK) return nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        *err = ORZ_ECUDA;
+        return nullptr;
+    }
+    orz_batch *b = new (std::nothrow) orz_batch();
+    if (!b) {
+        *err = ORZ_ENOMEM;
+        return nullptr;
+    }
+    b->device = device;
+    b->mode = mode;
+    b->n = n;
+    b->chunk_mode = chunk_mode;
+    if (cfg) b->cfg = *cfg;
+    b->d_in.resize(n);
+    b->d_out.resize(n);
+    b->in_cap.resize(n);
+    b->in_len.assign(n, 0);
+    b->out_cap.resize(n);
+    b->zero_lo.resize(n);
+    b->zero_hi.resize(n);
+    b->heads.resize(n);
+    b->status.assign(n, 0);
+    b->result_len.assign(n, 0);
+
+    ArenaPlan plan;
+    struct Offs {
+        size_t in, out, win, nodes, heads, words, symranks, items, sorted, payload, zero_lo, zero_hi;
+        size_t win_alloc;
+        uint32_t win_lo, win_hi, items_cap, payload_cap;
+    };
+    std::vector<Offs> offs(n);
+    const size_t ctl_off = plan.take(mode == 0 ? sizeof(EncStream) * n : sizeof(DecStream) * n);
+    for (int i = 0; i < n; i++) {
+        Offs &o = offs[i];
+        const size_t len = in_len[i];
+        b->in_cap[i] = len;
+        b->out_cap[i] = out_cap[i];
+        o.in = plan.take(len + 64);
+        if (mode == 0) {
+            o.out = plan.take(out_cap[i] + 64);
+            const bool one_block = !chunk_mode && len <= kBlockNew;
+            if (one_block) { // only positions near [PREMATCH, PREMATCH+len) are ever touched
+                o.win_lo = (kPrematch - kSentinel) & ~15u;
+                o.win_hi = (uint32_t)(kPrematch + len + kSentinel + kWinSlack);
+            } else {
+                o.win_lo = 0;
+                o.win_hi = kBlockSize + kSentinel + kWinSlack;
+            }
+            o.items_cap = chunk_mode ? kChunkItems : (uint32_t)(len < kChunkItems ? (len ? len : 1) : kChunkItems);
+            o.payload_cap = (uint32_t)align_up((size_t)o.items_cap * 5 + 16384, 16);
+            // zero-initialised state: window, nodes, words (heads are 0xff, handled separately)
+            o.zero_lo = plan.take(0, 256);
+            o.win_alloc = (o.win_lo == 0 ? kSentinel : 0) + (size_t)(o.win_hi - o.win_lo);
+            o.win = plan.take(o.win_alloc, 256);
+            o.nodes = plan.take(sizeof(Node) * kNumBuckets * kNodesStride);
+            o.words = plan.take(65536);
+            o.zero_hi = plan.take(0, 256);
+            o.heads = plan.take(sizeof(int16_t) * kNumBuckets * kHeadsStride);
+            o.symranks = plan.take(sizeof(SymRank) * kNumCtx);
+            o.items = plan.take(sizeof(Item) * o.items_cap);
+            o.sorted = plan.take(sizeof(uint32_t) * o.items_cap);
+            o.payload = plan.take(o.payload_cap);
+        } else {
+            o.zero_lo = plan.take(0, 256);
+            // stream mode decodes in place: 256 zero bytes precede out[0]; chunk mode keeps the lib.rs:102 window
+            const size_t out_bytes = chunk_mode ? (size_t)kSentinel + kBlockSize + kSentinel + 64 : 256 + out_cap[i] + 64;
+            o.out = plan.take(out_bytes, 256);
+            o.nodes = plan.take(sizeof(Node) * kNumBuckets * kNodesStride);
+            o.words = plan.take(65536);
+            o.zero_hi = plan.take(0, 256);
+            o.symranks = plan.take(sizeof(SymRank) * kNumCtx);
+        }
+    }
+    b->arena_size = align_up(plan.off, 256);
+    if (cudaMalloc(&b->arena, b->arena_size) != cudaSuccess) {
+        cudaGetLastError();
+        *err = ORZ_ENOMEM;
+        delete b;
+        return nullptr;
+    }
+    if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost(&b->h_status_pinned, sizeof(int32_t) * n) != cudaSuccess) {
+        *err = ORZ_ECUDA;
+        batch_destroy(b);
+        return nullptr;
+    }
+    uint8_t *A = b->arena;
+    if (mode == 0) {
+        b->d_enc = reinterpret_cast<EncStream *>(A + ctl_off);
+        b->enc.resize(n);
+        for (int i = 0; i < n; i++) {
+            const Offs &o = offs[i];
+            EncStream &S = b->enc[i];
+            memset(&S, 0, sizeof S);
+            S.in = A + o.in;
+            S.in_len = 0;
+            S.out = A + o.out;
+            S.out_cap = out_cap[i];
+            S.win = (o.win_lo == 0) ? (A + o.win + kSentinel) : (A + o.win - o.win_lo);
+            S.win_lo = o.win_lo;
+            S.win_hi = o.win_hi;
+            S.nodes = reinterpret_cast<Node *>(A + o.nodes);
+            S.heads = reinterpret_cast<int16_t *>(A + o.heads);
+            S.words = reinterpret_cast<uint16_t *>(A + o.words);
+            S.symranks = reinterpret_cast<SymRank *>(A + o.symranks);
+            S.items = reinterpret_cast<Item *>(A + o.items);
+            S.sorted = reinterpret_cast<uint32_t *>(A + o.sorted);
+            S.payload = A + o.payload;
+            S.payload_cap = o.payload_cap;
+            S.items_cap = o.items_cap;
+            S.depth0 = (uint32_t)(cfg->match_depth > 0x7fffffffu ? 0x7fffffffu : cfg->match_depth);
+            S.depth1 = (uint32_t)(cfg->lazy_match_depth1 > 0x7fffffffu ? 0x7fffffffu : cfg->lazy_match_depth1);
+            S.depth2 = (uint32_t)(cfg->lazy_match_depth2 > 0x7fffffffu ? 0x7fffffffu : cfg->lazy_match_depth2);
+            S.self_driven = chunk_mode ? 0 : 1;
+            S.first_block = 1;   // lz.rs:63
+            S.after_literal = 1; // lz.rs:64
+            b->d_in[i] = A + o.in;
+            b->d_out[i] = A + o.out;
+            b->zero_lo[i] = A + o.zero_lo;
+            b->zero_hi[i] = A + o.zero_hi;
+            b->heads[i] = S.heads;
+        }
+    } else {
+        b->d_dec = reinterpret_cast<DecStream *>(A + ctl_off);
+        b->dec.resize(n);
+        for (int i = 0; i < n; i++) {
+            const Offs &o = offs[i];
+            DecStream &S = b->dec[i];
+            memset(&S, 0, sizeof S);
+            S.in = A + o.in;
+            S.in_len = 0;
+            S.out = chunk_mode ? nullptr : A + o.out + 256;
+            S.out_cap = out_cap[i];
+            S.win = chunk_mode ? A + o.out + kSentinel : nullptr;
+            S.nodes = reinterpret_cast<Node *>(A + o.nodes);
+            S.words = reinterpret_cast<uint16_t *>(A + o.words);
+            S.symranks = reinterpret_cast<SymRank *>(A + o.symranks);
+            S.self_driven = chunk_mode ? 0 : 1;
+            S.first_block = 1;
+            S.after_literal = 1;
+            S.spos = kPrematch;
+            b->d_in[i] = A + o.in;
+            b->d_out[i] = chunk_mode ? S.win : S.out;
+            b->zero_lo[i] = A + o.zero_lo;
+            b->zero_hi[i] = A + o.zero_hi;
+            b->heads[i] = nullptr;
+        }
+    }
+    return b;
+}
+
+// LZEncoder::new / LZDecoder::new + buffer allocation of lib.rs:67-70,102-105: everything zero, heads -1
+static int batch_reset_state(orz_batch *b) {
+    for (int i = 0; i < b->n; i++) {
+        CU_TRY(cudaMemsetAsync(b->zero_lo[i], 0, (size_t)(b->zero_hi[i] - b->zero_lo[i]), b->st));
+        if (b->mode == 0)
+            CU_TRY(cudaMemsetAsync(b->heads[i], 0xff, sizeof(int16_t) * kNumBuckets * kHeadsStride, b->st));
+    }
+    if (b->mode == 0) {
+        for (int i = 0; i < b->n; i++) b->enc[i].in_len = b->in_len[i];
+        CU_TRY(cudaMemcpyAsync(b->d_enc, b->enc.data(), sizeof(EncStream) * b->n, cudaMemcpyHostToDevice, b->st));
+    } else {
+        for (int i = 0; i < b->n; i++) b->dec[i].in_len = b->in_len[i];
+        CU_TRY(cudaMemcpyAsync(b->d_dec, b->dec.data(), sizeof(DecStream) * b->n, cudaMemcpyHostToDevice, b->st));
+    }
+    return ORZ_OK;
+}
+
+static int fetch_status(orz_batch *b, bool *all_done) {
+    const void *src = b->mode == 0 ? (const void *)&b->d_enc[0].status : (const void *)&b->d_dec[0].status;
+    const size_t pitch = b->mode == 0 ? sizeof(EncStream) : sizeof(DecStream);
+    CU_TRY(cudaMemcpy2DAsync(b->h_status_pinned, sizeof(int32_t), src, pitch, sizeof(int32_t), b->n, cudaMemcpyDeviceToHost, b->st));
+    CU_TRY(cudaStreamSynchronize(b->st));
+    *all_done = true;
+    for (int i = 0; i < b->n; i++) {
+        b->status[i] = b->h_status_pinned[i];
+        if (b->status[i] == 0) *all_done = false;
+    }
+    return ORZ_OK;
+}
+
+extern "C" orz_batch *orz_batch_create(int device, int mode, const orz_lzcfg *cfg, int nstreams, const size_t *in_len,
+                                       const size_t *out_cap) {
+    int err;
+    if (!in_len || !out_cap || (mode != 0 && mode != 1)) return nullptr;
+    return batch_create(device, mode, cfg, nstreams, in_len, out_cap, false, &err);
+}
+extern "C" void orz_batch_free(orz_batch *b) { batch_destroy(b); }
+
+extern "C" int orz_batch_upload(orz_batch *b, int i, const uint8_t *host, size_t n) {
+    if (!b || i < 0 || i >= b->n || n > b->in_cap[i] || (n && !host)) return ORZ_EARG;
+    CU_TRY(cudaSetDevice(b->device));
+    if (n) CU_TRY(cudaMemcpyAsync(b->d_in[i], host, n, cudaMemcpyHostToDevice, b->st));
+    CU_TRY(cudaMemsetAsync(b->d_in[i] + n, 0, 64, b->st));
+    b->in_len[i] = n;
+    return ORZ_OK;
+}
+
+extern "C" int orz_batch_run(orz_batch *b) {
+    if (!b) return ORZ_EARG;
+    CU_TRY(cudaSetDevice(b->device));
+    b->timer.reset();
+    int rc = batch_reset_state(b);
+    if (rc) return rc;
+    bool all_done = false;
+    if (b->mode == 0) {
+        int id = b->timer.begin(2, b->st);
+        launch_enc_begin(b->d_enc, b->n, b->st);
+        b->timer.end(id, b->st);
+        for (;;) {
+            if ((rc = fetch_status(b, &all_done))) return rc;
+            if (all_done) break;
+            id = b->timer.begin(0, b->st);
+            launch_parse(b->d_enc, b->n, b->st);
+            b->timer.end(id, b->st);
+            id = b->timer.begin(1, b->st);
+            launch_emit(b->d_enc, b->n, b->st);
+            b->timer.end(id, b->st);
+            CU_TRY(cudaGetLastError());
+        }
+        // result lengths
+        std::vector<EncStream> tmp(b->n);
+        CU_TRY(cudaMemcpyAsync(tmp.data(), b->d_enc, sizeof(EncStream) * b->n, cudaMemcpyDeviceToHost, b->st));
+        CU_TRY(cudaStreamSynchronize(b->st));
+        for (int i = 0; i < b->n; i++) b->result_len[i] = tmp[i].out_pos;
+    } else {
+        int id = b->timer.begin(3, b->st);
+        launch_decode(b->d_dec, b->n, b->st);
+        b->timer.end(id, b->st);
+        CU_TRY(cudaGetLastError());
+        std::vector<DecStream> tmp(b->n);
+        CU_TRY(cudaMemcpyAsync(tmp.data(), b->d_dec, sizeof(DecStream) * b->n, cudaMemcpyDeviceToHost, b->st));
+        CU_TRY(cudaStreamSynchronize(b->st));
+        for (int i = 0; i < b->n; i++) {
+            b->result_len[i] = tmp[i].out_len;
+            b->status[i] = tmp[i].status;
+        }
+    }
+    b->timer.collect();
+    b->ran = true;
+    for (int i = 0; i < b->n; i++)
+        if (b->status[i] < 0) return b->status[i];
+    return ORZ_OK;
+}
+
+extern "C" int orz_batch_result_len(orz_batch *b, int i, size_t *len) {
+    if (!b || i < 0 || i >= b->n || !len || !b->ran) return ORZ_EARG;
+    if (b->status[i] < 0) return b->status[i];
+    *len = (size_t)b->result_len[i];
+    return ORZ_OK;
+}
+
+extern "C" int orz_batch_download(orz_batch *b, int i, uint8_t *host, size_t cap, size_t *len) {
+    if (!b || i < 0 || i >= b->n || !b->ran) return ORZ_EARG;
+    if (b->status[i] < 0) return b->status[i];
+    const size_t n = (size_t)b->result_len[i];
+    if (n > cap) return ORZ_ENOSPC;
+    CU_TRY(cudaSetDevice(b->device));
+    if (n) CU_TRY(cudaMemcpyAsync(host, b->d_out[i], n, cudaMemcpyDeviceToHost, b->st));
+    CU_TRY(cudaStreamSynchronize(b->st));
+    if (len) *len = n;
+    return ORZ_OK;
+}
+
+extern "C" void *orz_batch_result_dev(orz_batch *b, int i) {
+    if (!b || i < 0 || i >= b->n) return nullptr;
+    return b->d_out[i];
+}
+
+extern "C" int orz_batch_timing(orz_batch *b, int cls, float *total_ms, int *launches) {
+    if (!b || cls < 0 || cls > 3) return 0;
+    if (total_ms) *total_ms = b->timer.ms[cls];
+    if (launches) *launches = b->timer.launches[cls];
+    return b->timer.launches[cls];
+}
+
+// ------------------------------------------------------------------------------------------------
+// stream / batch entry points with host buffers (lib.rs:58-92, 94-129)
+// ------------------------------------------------------------------------------------------------
+static int run_host_batch(int device, int mode, const orz_lzcfg *cfg, int n, const uint8_t *const *in, const size_t *in_len,
+                          uint8_t *const *out, const size_t *out_cap, size_t *out_len) {
+    if (n <= 0 || !in || !in_len || !out || !out_cap || !out_len) return ORZ_EARG;
+    int err;
+    std::vector<size_t> dev_cap(out_cap, out_cap + n);
+    orz_batch *b = batch_create(device, mode, cfg, n, in_len, dev_cap.data(), false, &err);
+    if (!b) return err;
+    int rc = ORZ_OK;
+    for (int i = 0; i < n && rc == ORZ_OK; i++) rc = orz_batch_upload(b, i, in[i], in_len[i]);
+    if (rc == ORZ_OK) rc = orz_batch_run(b);
+    if (rc == ORZ_OK)
+        for (int i = 0; i < n && rc == ORZ_OK; i++) rc = orz_batch_download(b, i, out[i], out_cap[i], &out_len[i]);
+    batch_destroy(b);
+    return rc;
+}
+
+extern "C" int orz_encode_batch(int device, const orz_lzcfg *cfg, int nstreams, const uint8_t *const *in, const size_t *n,
+                                uint8_t *const *out, const size_t *out_cap, size_t *out_len) {
+    if (!cfg) return ORZ_EARG;
+    return run_host_batch(device, 0, cfg, nstreams, in, n, out, out_cap, out_len);
+}
+extern "C" int orz_decode_batch(int device, int nstreams, const uint8_t *const *in, const size_t *n, uint8_t *const *out,
+                                const size_t *out_cap, size_t *out_len) {
+    return run_host_batch(device, 1, nullptr, nstreams, in, n, out, out_cap, out_len);
+}
+extern "C" int orz_encode_stream(int device, const orz_lzcfg *cfg, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
+                                 size_t *out_len) {
+    return orz_encode_batch(device, cfg, 1, &in, &n, &out, &out_cap, out_len);
+}
+extern "C" int orz_decode_stream(int device, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *out_len) {
+    return orz_decode_batch(device, 1, &in, &n, &out, &out_cap, out_len);
+}
+
+// ------------------------------------------------------------------------------------------------
+// operator interface (lz.rs:75-95, 353-366): host drives chunks, codec state stays in HBM
+// ------------------------------------------------------------------------------------------------
+struct orz_lzenc {
+    orz_batch *b;
+    const uint8_t *last_sbuf;
+    size_t last_len, last_spos;
+    bool started;
+};
+struct orz_lzdec {
+    orz_batch *b;
+    size_t in_cap;
+    bool started;
+};
+
+extern "C" orz_lzenc *orz_lzenc_new(int device) {
+    int err;
+    orz_lzcfg cfg = {45, 27, 18};
+    size_t in_len = 0, out_cap = 0;
+    orz_batch *b = batch_create(device, 0, &cfg, 1, &in_len, &out_cap, true, &err);
+    if (!b) return nullptr;
+    if (batch_reset_state(b) != ORZ_OK || cudaStreamSynchronize(b->st) != cudaSuccess) {
+        batch_destroy(b);
+        return nullptr;
+    }
+    orz_lzenc *e = new (std::nothrow) orz_lzenc{b, nullptr, 0, 0, false};
+    if (!e) batch_destroy(b);
+    return e;
+}
+extern "C" void orz_lzenc_free(orz_lzenc *e) {
+    if (!e) return;
+    batch_destroy(e->b);
+    delete e;
+}
+extern "C" int orz_lzenc_forward(orz_lzenc *e, size_t forward_len) {
+    if (!e) return ORZ_EARG;
+    orz_batch *b = e->b;
+    CU_TRY(cudaSetDevice(b->device));
+    launch_enc_forward(b->d_enc, (uint32_t)(forward_len > 0x1ffffffu ? 0x1ffffffu : forward_len), b->st);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(b->st));
+    e->last_sbuf = nullptr; // the caller slid its window (lib.rs:83): force a re-upload
+    return ORZ_OK;
+}
+extern "C" int orz_lzenc_encode(orz_lzenc *e, const orz_lzcfg *cfg, const uint8_t *sbuf, size_t sbuf_len, uint8_t *tbuf,
+                                size_t tbuf_cap, size_t spos, size_t *spos_out, size_t *tlen_out) {
+    if (!e || !cfg || !sbuf || !tbuf || !spos_out || !tlen_out) return ORZ_EARG;
+    if (sbuf_len > kBlockSize || spos >= sbuf_len || spos < 4) return ORZ_EARG;
+    orz_batch *b = e->b;
+    CU_TRY(cudaSetDevice(b->device));
+    EncStream &H = b->enc[0];
+    const bool cont = e->started && sbuf == e->last_sbuf && sbuf_len == e->last_len && spos == e->last_spos && spos != kPrematch;
+    if (!cont) { // (re)upload the window including both sentinels: those bytes are bit-visible
+        CU_TRY(cudaMemcpyAsync(H.win - kSentinel, sbuf - kSentinel, sbuf_len + 2 * (size_t)kSentinel, cudaMemcpyHostToDevice, b->st));
+    }
+    // patch the control block: cfg, spos, sbuf_len
+    struct Patch {
+        uint32_t depth0, depth1, depth2;
+    } p;
+    p.depth0 = (uint32_t)(cfg->match_depth > 0x7fffffffu ? 0x7fffffffu : cfg->match_depth);
+    p.depth1 = (uint32_t)(cfg->lazy_match_depth1 > 0x7fffffffu ? 0x7fffffffu : cfg->lazy_match_depth1);
+    p.depth2 = (uint32_t)(cfg->lazy_match_depth2 > 0x7fffffffu ? 0x7fffffffu : cfg->lazy_match_depth2);
+    CU_TRY(cudaMemcpyAsync(&b->d_enc[0].depth0, &p, sizeof p, cudaMemcpyHostToDevice, b->st));
+    uint32_t ss[2] = {(uint32_t)spos, (uint32_t)sbuf_len};
+    CU_TRY(cudaMemcpyAsync(&b->d_enc[0].spos, ss, sizeof ss, cudaMemcpyHostToDevice, b->st));
+    launch_parse(b->d_enc, 1, b->st);
+    launch_emit(b->d_enc, 1, b->st);
+    CU_TRY(cudaGetLastError());
+    EncStream R;
+    CU_TRY(cudaMemcpyAsync(&R, b->d_enc, sizeof R, cudaMemcpyDeviceToHost, b->st));
+    CU_TRY(cudaStreamSynchronize(b->st));
+    if (R.status < 0) return R.status;
+    if (R.payload_len > tbuf_cap) return ORZ_ENOSPC;
+    CU_TRY(cudaMemcpyAsync(tbuf, H.payload, R.payload_len, cudaMemcpyDeviceToHost, b->st));
+    CU_TRY(cudaStreamSynchronize(b->st));
+    *spos_out = R.spos;
+    *tlen_out = R.payload_len;
+    e->started = true;
+    e->last_sbuf = sbuf;
+    e->last_len = sbuf_len;
+    e->last_spos = R.spos;
+    return ORZ_OK;
+}
+
+extern "C" orz_lzdec *orz_lzdec_new(int device) {
+    int err;
+    size_t in_len = (size_t)kTbufLen, out_cap = kBlockSize; // lib.rs:103: payloads are < 3*PREMATCH bytes
+    orz_batch *b = batch_create(device, 1, nullptr, 1, &in_len, &out_cap, true, &err);
+    if (!b) return nullptr;
+    if (batch_reset_state(b) != ORZ_OK || cudaStreamSynchronize(b->st) != cudaSuccess) {
+        batch_destroy(b);
+        return nullptr;
+    }
+    orz_lzdec *d = new (std::nothrow) orz_lzdec{b, in_len, false};
+    if (!d) batch_destroy(b);
+    return d;
+}
+extern "C" void orz_lzdec_free(orz_lzdec *d) {
+    if (!d) return;
+    batch_destroy(d->b);
+    delete d;
+}
+extern "C" int orz_lzdec_forward(orz_lzdec *d, size_t forward_len) {
+    if (!d) return ORZ_EARG;
+    orz_batch *b = d->b;
+    CU_TRY(cudaSetDevice(b->device));
+    if (forward_len == 0) return ORZ_OK;
+    if (forward_len > kBlockSize) forward_len = kBlockSize;
+    // mirror the caller's copy_within (lib.rs:121) on the device window, then rebase the ring (lz.rs:359-364)
+    uint8_t *win = b->dec[0].win;
+    const size_t keep = kBlockSize - forward_len;
+    if (keep > 0) {
+        if (keep <= forward_len) {
+            CU_TRY(cudaMemcpyAsync(win, win + forward_len, keep, cudaMemcpyDeviceToDevice, b->st));
+        } else { // overlapping ranges: stage through a temporary
+            uint8_t *tmp = nullptr;
+            CU_TRY(cudaMalloc(&tmp, keep));
+            cudaMemcpyAsync(tmp, win + forward_len, keep, cudaMemcpyDeviceToDevice, b->st);
+            cudaMemcpyAsync(win, tmp, keep, cudaMemcpyDeviceToDevice, b->st);
+            cudaStreamSynchronize(b->st);
+            cudaFree(tmp);
+        }
+    }
+    launch_dec_forward(b->d_dec, (uint32_t)forward_len, b->st);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(b->st));
+    return ORZ_OK;
+}
+extern "C" int orz_lzdec_decode(orz_lzdec *d, const uint8_t *tbuf, size_t tlen, uint8_t *sbuf, size_t sbuf_cap, size_t spos,
+                                size_t *spos_end) {
+    if (!d || !tbuf || !sbuf || !spos_end) return ORZ_EARG;
+    if (tlen == 0 || tlen >= kTbufLen) return ORZ_EINVAL; // lib.rs:111-113
+    if (spos < 4 || spos > kBlockSize || sbuf_cap < kBlockSize) return ORZ_EARG;
+    orz_batch *b = d->b;
+    CU_TRY(cudaSetDevice(b->device));
+    CU_TRY(cudaMemcpyAsync(b->d_in[0], tbuf, tlen, cudaMemcpyHostToDevice, b->st));
+    CU_TRY(cudaMemsetAsync(b->d_in[0] + tlen, 0, 16, b->st));
+    uint64_t il = tlen;
+    CU_TRY(cudaMemcpyAsync(&b->d_dec[0].in_len, &il, sizeof il, cudaMemcpyHostToDevice, b->st));
+    uint32_t sp = (uint32_t)spos;
+    CU_TRY(cudaMemcpyAsync(&b->d_dec[0].spos, &sp, sizeof sp, cudaMemcpyHostToDevice, b->st));
+    launch_decode(b->d_dec, 1, b->st);
+    CU_TRY(cudaGetLastError());
+    DecStream R;
+    CU_TRY(cudaMemcpyAsync(&R, b->d_dec, sizeof R, cudaMemcpyDeviceToHost, b->st));
+    CU_TRY(cudaStreamSynchronize(b->st));
+    if (R.status < 0) {
+        int32_t zero = 0; // leave the decoder usable for diagnostics; the stream itself is broken
+        cudaMemcpyAsync(&b->d_dec[0].status, &zero, sizeof zero, cudaMemcpyHostToDevice, b->st);
+        cudaStreamSynchronize(b->st);
+        return R.status;
+    }
+    if (R.spos < spos || R.spos > kBlockSize) return ORZ_EINVAL;
+    CU_TRY(cudaMemcpyAsync(sbuf + spos, b->dec[0].win + spos, R.spos - spos, cudaMemcpyDeviceToHost, b->st));
+    CU_TRY(cudaStreamSynchronize(b->st));
+    *spos_end = R.spos;
+    return ORZ_OK;
+}

@@ -1,0 +1,514 @@
+// decode_kernels.cu — sm_100a kernel of the ROLZ decoder (lz.rs:366-478, lib.rs:94-129).
+//
+// Decoding one orz stream is a strictly serial chain: the bit position of item n+1 depends on the
+// rank-decoded value of item n, which depends on bytes already produced.  One warp owns one stream;
+// lane 0 runs the item chain, all 32 lanes build the per-chunk decode tables, initialise the rank
+// tables and rebase the ring at block boundaries.  Throughput comes from many streams in flight.
+#include "orz_dev.cuh"
+
+namespace orz {
+
+constexpr int kLutBits = 11;
+constexpr int kLutSize = 1 << kLutBits;
+
+struct HuffDec {
+    uint16_t lut[kLutSize];          // sym | len << 9 for codes of <= kLutBits bits, 0 otherwise
+    uint16_t sorted[kSymStride + 8]; // symbols in (len, sym) order (huffman.rs:130)
+    uint16_t first_code[16];
+    uint16_t count[16];
+    uint16_t offs[16];
+    uint8_t lens[kSymStride + 8];
+    int n;
+    int ok;
+};
+
+struct DecShared {
+    HuffDec h[3];
+    uint16_t bhead[kNumBuckets];
+    uint16_t vs[kSymStride + 8];
+    uint32_t num_counted;
+};
+
+struct BitReader { // coder.rs:91-157,159-196
+    const uint8_t *base; // 4 B aligned
+    uint64_t pos;        // byte offset of the next refill
+    uint64_t bb;
+    int bl;
+    __device__ __forceinline__ void refill() {
+        if (bl < 32) {
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(base + (pos & ~3ull));
+            const uint32_t w = bswap32(__funnelshift_r(wp[0], wp[1], ((uint32_t)pos & 3u) * 8u));
+            bb = (bb << 32) | w;
+            bl += 32;
+            pos += 4;
+        }
+    }
+    __device__ __forceinline__ uint32_t get(int n) {
+        refill();
+        bl -= n;
+        return (uint32_t)(bb >> bl) & ((1u << n) - 1u);
+    }
+    __device__ uint32_t varint() { // coder.rs:108-120
+        uint32_t v = 0;
+        for (uint32_t sh = 0;; sh++) {
+            const uint32_t b = get(2);
+            if (sh < 32) v |= (b & 1u) << sh;
+            if (!(b > 1)) break;
+            if (sh > 40) break; // malformed
+        }
+        return v;
+    }
+};
+
+// coder.rs:127-142 — lane 0 only
+__device__ void read_table(BitReader &br, HuffDec &h) {
+    const uint32_t maxl = br.varint();
+    int n = 0;
+    h.ok = maxl <= 15;
+    for (;;) {
+        const uint32_t delta = br.varint();
+        if (delta == 0) break;
+        if ((uint32_t)n + delta > (uint32_t)kSymStride) {
+            h.ok = 0;
+            break;
+        }
+        for (uint32_t k = 1; k < delta; k++) h.lens[n++] = 0;
+        const uint32_t d = br.varint();
+        if (d > maxl) h.ok = 0; // the reference would wrap a u8 here; a well-formed table never does
+        const uint32_t l = maxl - d;
+        h.lens[n++] = (uint8_t)(l & 15u);
+    }
+    h.n = n;
+}
+
+// huffman.rs:119-141,150-167 — canonical codes -> primary LUT + (first_code,count,offs,sorted) for long codes
+__device__ void build_table(HuffDec &h, int lane) {
+    for (int i = lane; i < kLutSize; i += 32) h.lut[i] = 0;
+    if (lane == 0) {
+        for (int l = 0; l < 16; l++) h.count[l] = 0;
+        for (int s = 0; s < h.n; s++) h.count[h.lens[s]]++;
+        h.count[0] = 0;
+        uint32_t code = 0, off = 0;
+        for (int l = 1; l <= 15; l++) {
+            h.first_code[l] = (uint16_t)code;
+            h.offs[l] = (uint16_t)off;
+            code = (code + h.count[l]) << 1;
+            off += h.count[l];
+            if (code > (2u << l)) h.ok = 0; // over-subscribed code
+        }
+        uint16_t fill[16];
+        for (int l = 1; l <= 15; l++) fill[l] = h.offs[l];
+        for (int s = 0; s < h.n; s++) {
+            const int l = h.lens[s];
+            if (l) h.sorted[fill[l]++] = (uint16_t)s;
+        }
+    }
+    __syncwarp();
+    if (!h.ok) return;
+    for (int l = 1; l <= kLutBits; l++) {
+        const int cnt = h.count[l];
+        const uint32_t fc = h.first_code[l];
+        const int span = 1 << (kLutBits - l);
+        for (int j = lane; j < cnt; j += 32) {
+            const uint16_t sym = h.sorted[h.offs[l] + j];
+            const uint32_t basei = (fc + j) << (kLutBits - l);
+            const uint16_t e = (uint16_t)(sym | (l << 9));
+            for (int q = 0; q < span; q++)
+                if (basei + q < (uint32_t)kLutSize) h.lut[basei + q] = e;
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ int decode_sym(BitReader &br, const HuffDec &h) { // coder.rs:144-150
+    br.refill();
+    const uint32_t peek = (uint32_t)(br.bb >> (br.bl - 15)) & 0x7fffu;
+    const uint32_t e = h.lut[peek >> (15 - kLutBits)];
+    if (e) {
+        br.bl -= (int)(e >> 9);
+        return (int)(e & 511u);
+    }
+    for (int l = kLutBits + 1; l <= 15; l++) {
+        const uint32_t d = (peek >> (15 - l)) - h.first_code[l];
+        if (d < h.count[l]) {
+            br.bl -= l;
+            return h.sorted[h.offs[l] + d];
+        }
+    }
+    return -1;
+}
+
+// symrank.rs:61-97 on a table in global memory
+__device__ __forceinline__ void symrank_update(SymRank *s, uint32_t v, uint32_t i) {
+    uint32_t ecnt = s->cnt, esum = s->sum;
+    if (ecnt > (uint32_t)kNumSym) {
+        ecnt = ecnt * 9 / 10;
+        esum = esum * 9 / 10;
+    }
+    ecnt += 1;
+    esum += i;
+    s->cnt = ecnt;
+    s->sum = esum;
+    const uint32_t sub = ((i >> 4) + ((esum >> 4) / ecnt)) & 0xffffu;
+    uint32_t next_i = i > sub ? i - sub : 0;
+    if (next_i < (i >> 1)) next_i = i >> 1;
+    const uint32_t d = i - next_i;
+    if (d == 1) {
+        const uint16_t nv1 = s->value[next_i];
+        s->index[v] = (uint16_t)next_i;
+        s->value[i] = nv1;
+        s->index[nv1] = (uint16_t)i;
+        s->value[next_i] = (uint16_t)v;
+    } else if (d > 1) {
+        const uint32_t ni2 = next_i, ni1 = next_i + d / 2;
+        const uint16_t nv1 = s->value[ni1];
+        const uint16_t nv2 = s->value[ni2];
+        s->value[i] = nv1;
+        s->index[nv1] = (uint16_t)i;
+        s->value[ni1] = nv2;
+        s->index[nv2] = (uint16_t)ni1;
+        s->value[ni2] = (uint16_t)v;
+        s->index[v] = (uint16_t)ni2;
+    }
+}
+
+__global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
+    DecStream *S = &streams[blockIdx.x];
+    if (S->status != 0) return;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
+    const int lane = threadIdx.x;
+
+    for (int i = lane; i < kNumBuckets; i += 32) sh.bhead[i] = (uint16_t)S->bhead[i];
+    Node *nodes = S->nodes;
+    uint16_t *words = S->words;
+    SymRank *symranks = S->symranks;
+    const bool self_driven = S->self_driven != 0;
+    const uint8_t *in = S->in;
+    const uint64_t in_len = S->in_len;
+    uint64_t in_pos = S->in_pos;
+    uint64_t out_len = S->out_len;       // stream mode: bytes produced so far
+    uint64_t blk_apos = 0;               // stream mode: absolute output offset of window position PREMATCH
+    uint32_t spos = self_driven ? kPrematch : S->spos;
+    uint32_t after_literal = S->after_literal;
+    uint32_t first_block = S->first_block;
+    uint32_t n_chunks = 0;
+    int status = 0;
+    __syncwarp();
+
+    for (;;) {
+        // ---- framing (lib.rs:108-114, ioutil.rs:60-76) ----
+        uint32_t t = 0;
+        if (self_driven) {
+            if (lane == 0) {
+                uint64_t factor = 1, tt = 0;
+                for (;;) {
+                    if (in_pos >= in_len) {
+                        status = -3; // UnexpectedEof
+                        break;
+                    }
+                    const uint32_t v = in[in_pos++];
+                    if (v < 128) {
+                        tt += v * factor;
+                        break;
+                    }
+                    tt += (v - 128) * factor;
+                    factor *= 128;
+                    if (factor > (1ull << 42)) {
+                        status = -1;
+                        break;
+                    }
+                }
+                if (status == 0) {
+                    if (tt == 0) status = 1;                      // EOF marker
+                    else if (tt >= kTbufLen) status = -1;         // lib.rs:111-113
+                    else if (in_pos + tt > in_len) status = -3;   // lib.rs:114
+                    t = (uint32_t)tt;
+                }
+            }
+            status = __shfl_sync(0xffffffffu, status, 0);
+            if (status != 0) break;
+            t = __shfl_sync(0xffffffffu, t, 0);
+            in_pos = __shfl_sync(0xffffffffu, in_pos, 0);
+        } else {
+            t = (uint32_t)in_len;
+        }
+
+        // ---- chunk header (lz.rs:372-409) ----
+        BitReader br;
+        br.base = in;
+        br.pos = self_driven ? in_pos : 0;
+        br.bb = 0;
+        br.bl = 0;
+        uint32_t sbuf_len = 0, n_items = 0;
+        if (lane == 0) {
+            if (first_block) {
+                uint32_t num = br.varint();
+                if (num > (uint32_t)kNumSym) status = -1;
+                else {
+                    for (int i = 0; i < kSymStride; i++) sh.h[0].lens[i] = 0; // borrow as the `set` array
+                    for (uint32_t i = 0; i < num; i++) {
+                        const uint32_t v = br.get(9);
+                        if (v >= (uint32_t)kNumSym || sh.h[0].lens[v]) {
+                            status = -1;
+                            break;
+                        }
+                        sh.vs[i] = (uint16_t)v;
+                        sh.h[0].lens[v] = 1;
+                    }
+                    if (status == 0)
+                        for (int i = 0; i < kNumSym; i++)
+                            if (!sh.h[0].lens[i]) sh.vs[num++] = (uint16_t)i;
+                }
+            }
+            if (status == 0) {
+                sbuf_len = br.varint();
+                n_items = br.varint();
+                read_table(br, sh.h[0]);
+                read_table(br, sh.h[1]);
+                read_table(br, sh.h[2]);
+                if (!sh.h[0].ok || !sh.h[1].ok || !sh.h[2].ok) status = -1;
+                if (n_items > kChunkItems || sbuf_len > kBlockSize) status = -1;
+            }
+        }
+        status = __shfl_sync(0xffffffffu, status, 0);
+        if (status != 0) break;
+        __syncwarp();
+        if (first_block) { // lz.rs:386-391
+            for (int tix = 0; tix < kNumCtx; tix++) {
+                SymRank *g = &symranks[tix];
+                for (int i = lane; i < kNumSym; i += 32) {
+                    const uint16_t v = sh.vs[i];
+                    g->value[i] = v;
+                    g->index[v] = (uint16_t)i;
+                }
+                if (lane == 0) {
+                    g->cnt = 0;
+                    g->sum = 1000000u;
+                }
+            }
+            first_block = 0;
+        }
+        build_table(sh.h[0], lane);
+        build_table(sh.h[1], lane);
+        build_table(sh.h[2], lane);
+        if (!sh.h[0].ok || !sh.h[1].ok || !sh.h[2].ok) {
+            status = -1;
+            break;
+        }
+        __threadfence_block();
+        __syncwarp();
+
+        // ---- items (lz.rs:411-476): the serial chain, lane 0 ----
+        const uint32_t spos_start = spos;
+        if (lane == 0) {
+            // window position p lives at win[p]; `wa`/`dl` give a 16 B aligned base for dword accesses
+            // (stream mode decodes in place: position PREMATCH of the current block is out[blk_apos]).
+            uint8_t *wa = self_driven ? (S->out + blk_apos - kBlockNew) : S->win;
+            const uint32_t dl = self_driven ? 1u : 0u;
+            uint8_t *win = wa + dl;
+            const uint64_t cap_pos = self_driven ? (uint64_t)kPrematch + (S->out_cap - blk_apos) : (uint64_t)kBlockSize;
+            const uint32_t lo_pos = self_driven ? (blk_apos >= kPrematch ? 0u : (uint32_t)(kPrematch - blk_apos)) : 0u;
+            const uint32_t limit = (uint32_t)(cap_pos < (uint64_t)kBlockSize ? cap_pos : (uint64_t)kBlockSize);
+            // bytes spos-4..spos-1, little endian (byte 3 = spos-1)
+            uint32_t prev4 = ld_u32_unaligned(wa, spos - 4 + dl);
+            for (uint32_t k = 0; k < n_items; k++) {
+                const uint32_t b_m1 = prev4 >> 24, b_m2 = (prev4 >> 16) & 0xffu, b_m3 = (prev4 >> 8) & 0xffu;
+                const uint32_t c = (b_m1 & 0x7fu) | is_alnum(b_m2) << 7;
+                const uint32_t h2 = (b_m1 & 0x7fu) | ((b_m2 & 0x7fu) | is_alnum(b_m3) << 7) << 7;
+                const uint32_t lwe = words[h2];
+                SymRank *sr = &symranks[c | after_literal << 8];
+                const uint32_t iun = sr->index[lwe & 0xffu];
+                const int sym = decode_sym(br, sh.h[after_literal]);
+                if (sym < 0) {
+                    status = -1;
+                    break;
+                }
+                const uint32_t i = (sym == kNumSym - 1) ? iun : (uint32_t)sym + ((uint32_t)sym >= iun); // symrank.rs:49-55
+                if (i >= (uint32_t)kNumSym) {
+                    status = -1;
+                    break;
+                }
+                const uint32_t v = sr->value[i];
+                symrank_update(sr, v, i);
+
+                Node *bn = nodes + c * kNodesStride;
+                const uint32_t head = sh.bhead[c];
+                const uint32_t new_head = head + 1 == kRing ? 0 : head + 1;
+                Node nn;
+                nn.pl = spos & 0x1ffffffu;
+                nn.next = -1;
+                nn.pad = 0;
+                if (v == (uint32_t)kWordSym) { // lz.rs:425-430
+                    if (spos + 2 > limit) {
+                        status = -2;
+                        break;
+                    }
+                    nn.expected = 0;
+                    bn[new_head] = nn;
+                    sh.bhead[c] = (uint16_t)new_head;
+                    after_literal = 0;
+                    win[spos] = (uint8_t)(lwe & 0xffu);
+                    win[spos + 1] = (uint8_t)(lwe >> 8);
+                    spos += 2;
+                    prev4 = (prev4 >> 16) | lwe << 16;
+                } else if (v < 256) { // lz.rs:431-437
+                    if (spos + 1 > limit) {
+                        status = -2;
+                        break;
+                    }
+                    nn.expected = 0;
+                    bn[new_head] = nn;
+                    sh.bhead[c] = (uint16_t)new_head;
+                    after_literal = 1;
+                    win[spos] = (uint8_t)v;
+                    spos += 1;
+                    const uint32_t y5 = prev4 & 0xffu; // byte spos'-5
+                    prev4 = (prev4 >> 8) | v << 24;    // bytes spos'-4 .. spos'-1
+                    const uint32_t y4 = prev4 & 0xffu, y3 = (prev4 >> 8) & 0xffu;
+                    const uint32_t hw = (y3 & 0x7fu) | ((y4 & 0x7fu) | is_alnum(y5) << 7) << 7; // hash2(spos'-3)
+                    words[hw] = (uint16_t)(prev4 >> 16);
+                } else { // lz.rs:438-474
+                    const uint32_t roid = (v - 256) / kLenidSize, lenid = (v - 256) % kLenidSize;
+                    const uint32_t robitlen = roid >> 1;
+                    const uint32_t ro = roid_base(roid) + (robitlen ? br.get((int)robitlen) : 0u);
+                    if (ro >= (uint32_t)kRing) {
+                        status = -1;
+                        break;
+                    }
+                    const uint32_t node = (head + kRing - ro) % kRing;
+                    const uint32_t pl = bn[node].pl;
+                    uint32_t mexp = bn[node].expected;
+                    uint32_t eml = lenid;
+                    if (lenid == (uint32_t)(kLenidSize - 1)) {
+                        const int e2 = decode_sym(br, sh.h[2]);
+                        if (e2 < 0) {
+                            status = -1;
+                            break;
+                        }
+                        eml = (uint32_t)e2;
+                    }
+                    const uint32_t mpos = node_pos(pl);
+                    uint32_t mmin = node_lenmin(pl);
+                    if (mmin < (uint32_t)kMatchMin) mmin = kMatchMin;
+                    if (mexp < (uint32_t)kMatchMin) mexp = kMatchMin;
+                    uint32_t mlen;
+                    if (eml + mmin > mexp) mlen = eml + mmin;
+                    else if (eml > 0) mlen = eml + mmin - 1;
+                    else mlen = mexp;
+                    if (mpos >= spos || mpos < lo_pos || mlen > 0x1ffu) {
+                        status = -1;
+                        break;
+                    }
+                    if (spos + mlen > limit) {
+                        status = -2;
+                        break;
+                    }
+                    // Bucket::update (matcher.rs:62-80)
+                    if (node_lenmin(pl) <= mlen) {
+                        const uint32_t lm = mlen + 1 < 127u ? mlen + 1 : 127u;
+                        bn[node].pl = mpos | lm << 25;
+                    }
+                    nn.expected = (uint8_t)mlen;
+                    bn[new_head] = nn;
+                    sh.bhead[c] = (uint16_t)new_head;
+                    after_literal = 0;
+                    // mem.rs:74-92: semantically a byte-serial overlapped copy
+                    const uint32_t dist = spos - mpos;
+                    if (dist >= 4) {
+                        for (uint32_t q = 0; q < mlen; q += 4) {
+                            const uint32_t wv = ld_u32_unaligned(wa, mpos + q + dl);
+                            const uint32_t left = mlen - q;
+                            win[spos + q] = (uint8_t)wv;
+                            if (left > 1) win[spos + q + 1] = (uint8_t)(wv >> 8);
+                            if (left > 2) win[spos + q + 2] = (uint8_t)(wv >> 16);
+                            if (left > 3) win[spos + q + 3] = (uint8_t)(wv >> 24);
+                        }
+                    } else {
+                        for (uint32_t q = 0; q < mlen; q++) win[spos + q] = win[mpos + q];
+                    }
+                    spos += mlen;
+                    const uint32_t t4 = ld_u32_unaligned(wa, spos - 5 + dl); // bytes spos-5 .. spos-2
+                    prev4 = ld_u32_unaligned(wa, spos - 4 + dl);
+                    const uint32_t y3 = (t4 >> 16) & 0xffu, y4 = (t4 >> 8) & 0xffu, y5 = t4 & 0xffu;
+                    const uint32_t hw = (y3 & 0x7fu) | ((y4 & 0x7fu) | is_alnum(y5) << 7) << 7;
+                    words[hw] = (uint16_t)(prev4 >> 16);
+                }
+            }
+            if (status == 0 && spos != sbuf_len) {
+                // lz.rs:477 returns min(spos, sbuf_len); a well-formed chunk ends exactly at sbuf_len
+                if (spos > sbuf_len) spos = sbuf_len;
+                else status = -1;
+            }
+        }
+        status = __shfl_sync(0xffffffffu, status, 0);
+        const uint32_t spos_end = __shfl_sync(0xffffffffu, spos, 0);
+        after_literal = __shfl_sync(0xffffffffu, after_literal, 0);
+        n_chunks++;
+        if (status != 0) break;
+        __threadfence_block();
+        __syncwarp();
+        if (!self_driven) {
+            spos = spos_end;
+            break;
+        }
+        out_len += spos_end - spos_start; // lib.rs:117
+        spos = spos_end;
+        in_pos += t;
+        if (spos >= kBlockSize) { // lib.rs:120-125: slide (a pointer shift here) + LZDecoder::forward (lz.rs:359-364)
+            if (spos > kBlockSize) {
+                status = -1;
+                break;
+            }
+            blk_apos += kBlockNew;
+            spos = kPrematch;
+            for (int i = lane; i < kNumBuckets * kNodesStride; i += 32) {
+                if ((i & (kNodesStride - 1)) >= kRing) continue;
+                const uint32_t pl = nodes[i].pl;
+                const uint32_t p = node_pos(pl);
+                nodes[i].pl = (p > kBlockNew ? p - kBlockNew : 0u) | (pl & 0xfe000000u);
+            }
+            __threadfence_block();
+            __syncwarp();
+        }
+    }
+
+    __syncwarp();
+    for (int i = lane; i < kNumBuckets; i += 32) S->bhead[i] = sh.bhead[i];
+    if (lane == 0) {
+        S->spos = spos;
+        S->after_literal = after_literal;
+        S->first_block = first_block;
+        S->out_len = out_len;
+        S->in_pos = in_pos;
+        S->n_chunks += n_chunks;
+        S->status = self_driven ? status : (status == 0 ? 0 : status);
+    }
+}
+
+// LZDecoder::forward for the chunk-level API (lz.rs:359-364) + device-side window slide (lib.rs:121)
+__global__ void __launch_bounds__(256) orz_dec_forward_kernel(DecStream *streams, uint32_t forward_len) {
+    DecStream *S = &streams[0];
+    Node *nodes = S->nodes;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int i = gid; i < kNumBuckets * kNodesStride; i += gsz) {
+        if ((i & (kNodesStride - 1)) >= kRing) continue;
+        const uint32_t pl = nodes[i].pl;
+        const uint32_t p = node_pos(pl);
+        nodes[i].pl = (p > forward_len ? p - forward_len : 0u) | (pl & 0xfe000000u);
+    }
+}
+
+void launch_decode(DecStream *d_streams, int n, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(orz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
+        attr_set = true;
+    }
+    orz_decode_kernel<<<n, 32, sizeof(DecShared), st>>>(d_streams);
+}
+void launch_dec_forward(DecStream *d_stream, uint32_t forward_len, cudaStream_t st) {
+    orz_dec_forward_kernel<<<148, 256, 0, st>>>(d_stream, forward_len);
+}
+
+} // namespace orz

@@ -1,0 +1,149 @@
+// orz_dev.cuh — shared device-side definitions for the B200 ROLZ codec kernels.
+//
+// Data layout in HBM (per stream) and the constants of the wire format.  Reference citations are
+// file:line into richox/orz @29414c6.  Nothing here is a translation of the Rust structs: the ring
+// node, chain link and "expected length" byte that the reference keeps in three arrays
+// (matcher.rs:28-31,102-105) are fused into one 8-byte record so that one chain hop is one load.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace orz {
+
+// ---- wire-format / algorithm constants -------------------------------------------------------
+constexpr uint32_t kBlockSize = (1u << 25) - 1;        // lib.rs:31  LZ_BLOCK_SIZE
+constexpr uint32_t kChunkItems = 1u << 20;             // lib.rs:32  LZ_CHUNK_SIZE
+constexpr int kMatchMax = 240;                         // lib.rs:33
+constexpr int kMatchMin = 4;                           // lib.rs:34
+constexpr uint32_t kSentinel = 480;                    // lib.rs:54
+constexpr uint32_t kPrematch = kBlockSize / 2;         // lib.rs:55  (16,777,215)
+constexpr uint32_t kBlockNew = kBlockSize - kPrematch; // new bytes per block (16,777,216)
+constexpr uint32_t kTbufLen = kPrematch * 3;           // lib.rs:68
+constexpr int kRing = 4094;                            // lz.rs:24   LZ_MF_BUCKET_ITEM_SIZE
+constexpr int kHashSize = 4627;                        // matcher.rs:18
+constexpr int kRoidSize = 22;                          // lz.rs:27
+constexpr int kLenidSize = 6;                          // lz.rs:28
+constexpr int kNumSym = 256 + kRoidSize * kLenidSize + 1; // lz.rs:25 (389)
+constexpr int kWordSym = kNumSym - 1;                  // lz.rs:29
+constexpr int kNumBuckets = 256;
+constexpr int kNumCtx = 512;
+
+// ---- HBM layout ---------------------------------------------------------------------------------
+constexpr int kNodesStride = 4096;  // ring slots per bucket, padded from 4094
+constexpr int kHeadsStride = 4640;  // hash heads per bucket, padded from 4627
+constexpr int kSymStride = 392;     // symbols per rank table, padded from 389
+constexpr uint32_t kWinSlack = 8192; // zero bytes kept readable after the window (tile loads)
+
+// One ring slot: pos:25 | match_len_min:7 (matcher.rs:231-237), chain link (matcher.rs:104), expected (matcher.rs:239-243)
+struct __align__(8) Node {
+    uint32_t pl;
+    int16_t next;
+    uint8_t expected;
+    uint8_t pad;
+};
+static_assert(sizeof(Node) == 8, "Node must be 8 bytes");
+
+__host__ __device__ __forceinline__ uint32_t node_pos(uint32_t pl) { return pl & 0x1ffffffu; }
+__host__ __device__ __forceinline__ uint32_t node_lenmin(uint32_t pl) { return pl >> 25; }
+
+// One parsed step (lz.rs:100-117 MatchItem), 16 bytes so a step is one st.v4
+struct __align__(16) Item {
+    uint16_t symbol;   // pre-rank symbol after stage A, rank after stage B
+    uint16_t ctx;      // symrank_context (9 bits)
+    uint16_t robits;
+    uint8_t unlikely;
+    uint8_t robitlen;
+    uint8_t eml;       // encoded_match_len
+    uint8_t flags;     // bit0 after_literal, bit1 is_match
+    uint16_t pad;
+    uint32_t seq;      // ordinal of this item among the chunk's items of the same ctx
+};
+static_assert(sizeof(Item) == 16, "Item must be 16 bytes");
+
+// symrank.rs:14-19
+struct SymRank {
+    uint16_t value[kSymStride];
+    uint16_t index[kSymStride];
+    uint32_t cnt;
+    uint32_t sum;
+};
+static_assert(sizeof(SymRank) == 1576, "SymRank size");
+
+// Per-stream encoder control block (lz.rs:49-80 LZContext+LZEncoder, lib.rs:64-90 loop state)
+struct EncStream {
+    // set by host
+    const uint8_t *in;    // whole input, HBM resident
+    uint64_t in_len;
+    uint8_t *out;         // framed orz stream
+    uint64_t out_cap;
+    uint8_t *win;         // win[p] is window position p (p may start at win_lo > 0 for one-block streams); 16 B aligned at p=0
+    uint32_t win_lo, win_hi;
+    Node *nodes;          // [256][kNodesStride]
+    int16_t *heads;       // [256][kHeadsStride]
+    uint16_t *words;      // [32768] two predicted bytes, little endian (lz.rs:52)
+    SymRank *symranks;    // [512]
+    Item *items;          // [items_cap]
+    uint32_t *sorted;     // [items_cap] item indices grouped by ctx
+    uint8_t *payload;     // chunk payload scratch, 4 B aligned
+    uint32_t payload_cap;
+    uint32_t items_cap;
+    uint32_t depth0, depth1, depth2; // LZCfg (lz.rs:32-37)
+    int32_t self_driven;  // 1: stream mode (kernel runs the lib.rs loop), 0: chunk mode (host drives)
+    // mutable
+    uint32_t bhead[kNumBuckets];
+    uint32_t ctx_count[kNumCtx];
+    uint32_t spos, sbuf_len, after_literal, first_block, n_items;
+    uint32_t payload_len;
+    uint64_t in_pos, out_pos;
+    int32_t status;       // 0 running, 1 done, <0 error code
+    uint32_t n_chunks;
+};
+
+// Per-stream decoder control block (lz.rs:348-357 LZDecoder, lib.rs:99-127 loop state)
+struct DecStream {
+    const uint8_t *in;    // framed orz stream (stream mode) or one chunk payload (chunk mode)
+    uint64_t in_len;
+    uint8_t *out;         // stream mode: out[0] is the first decoded byte; 16 readable zero bytes precede it
+    uint64_t out_cap;
+    uint8_t *win;         // chunk mode: win[p] = window position p
+    Node *nodes;          // [256][kNodesStride]  (chain link unused: the decoder keeps no hash chains, lz.rs:348-351)
+    uint16_t *words;
+    SymRank *symranks;
+    uint32_t bhead[kNumBuckets];
+    uint32_t spos;        // chunk mode: in/out
+    uint32_t after_literal, first_block;
+    int32_t self_driven;
+    uint64_t out_len;
+    uint64_t in_pos;
+    int32_t status;
+    uint32_t n_chunks;
+};
+
+// ---- small device helpers --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t is_alnum(uint32_t c) { // u8::is_ascii_alphanumeric
+    return (((c | 0x20u) - 'a') < 26u) | ((c - '0') < 10u);
+}
+// matcher.rs:255-263 on a little-endian dword
+__device__ __forceinline__ uint32_t hash_dword(uint32_t v) {
+    return ((v & 0xffu) * 131313131u ^ 797u) + (((v >> 8) & 0xffu) * 1313131u ^ 79797u) +
+           (((v >> 16) & 0xffu) * 13131u ^ 7979797u) + ((v >> 24) * 131u ^ 797979797u);
+}
+// unaligned little-endian dword from a 4-byte-aligned base (global or shared)
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *base, uint32_t off) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(base + (off & ~3u));
+    return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
+}
+// lz.rs:494-534: reduced offset -> (roid, extra bit count, extra bits).  base(id) = 2^(id/2) * (2 + (id&1)) - 2
+__device__ __forceinline__ void roid_encode(uint32_t ro, uint32_t &roid, uint32_t &bitlen, uint32_t &bits) {
+    uint32_t v = ro + 2;                       // v in [2, 4095]
+    uint32_t k = 31u - __clz(v);               // floor(log2 v) >= 1
+    uint32_t half = (v >> (k - 1)) & 1u;       // second-highest bit
+    roid = 2 * (k - 1) + half;
+    bitlen = k - 1;
+    bits = v & ((1u << (k - 1)) - 1u);
+}
+__device__ __forceinline__ uint32_t roid_base(uint32_t roid) { return ((2u + (roid & 1u)) << (roid >> 1)) - 2u; }
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+} // namespace orz
