@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric: encode MB/s on enwik8 at -l2, bit-identical output, beside the CPU path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload exact|segments]
+
+Workload (config.workload): BASELINE.json configs[1] — the 100,000,000-byte enwik8 corpus encoded at -l2 as ONE
+exact orz stream per GPU (byte-identical to `orz encode -l2 enwik8`).  One orz stream is a serial dependency
+chain and does not shard ("replicas only"), so --gpus N runs N independent replicas, one
+per rank, followed by one NCCL all-gather of the compressed spans; scaling is "weak".
+
+A step = one pass of the hot path over the whole input.
+  value : input resident in HBM, timed with CUDA events on the library's stream (state reset + all kernels).
+  e2e   : the public C-ABI call orz_encode_stream() with pinned HOST buffers (allocation, H2D, kernels, D2H inside).
+  roofline : the dominant kernel (orz_parse_kernel), algorithmic bytes (input read + stream written) over
+             its summed CUDA-event launch time, against the measured HBM peak in MEASURED_PEAKS.json.
+  cpu_baseline : the C oracle (a port of the reference; no Rust toolchain exists here) on this box's host cores.
+--impl reference times that oracle as the reference arm (the real Rust build cannot run on the GPU box).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_BYTES = 100_000_000
+LEVEL = 2
+METRIC = "encode MB/s on enwik8 at -l2, bit-identical output"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_encode_threads(data_list, level):
+    """Run the oracle on len(data_list) independent streams, one thread each (ctypes releases the GIL)."""
+    from oracle import pyoracle
+    outs = [None] * len(data_list)
+
+    def work(i):
+        outs[i] = pyoracle.encode(data_list[i], level)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(data_list))]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return time.perf_counter() - t0, outs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="exact", choices=["exact", "segments"])
+    ap.add_argument("--segment-bytes", type=int, default=1 << 20)
+    ap.add_argument("--bytes", type=int, default=N_BYTES, help="debug only: shrink the corpus (prints invalid:true)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = args.gpus
+    from tools import textgen
+    data, data_desc = textgen.corpus(args.bytes)
+    if args.workload == "exact":
+        streams = [data]
+        wl = f"BASELINE configs[1]: {args.bytes:,} B corpus as one exact orz stream per GPU, -l{LEVEL}"
+    else:
+        sb = args.segment_bytes
+        streams = [data[i:i + sb] for i in range(0, data.size, sb)]
+        wl = (f"segment-parallel (extension): {args.bytes:,} B corpus as {len(streams)} independent orz streams of "
+              f"{sb:,} B per GPU, -l{LEVEL}")
+    config = {"workload": wl, "level": LEVEL, "mode": "exact-stream" if args.workload == "exact" else "segment-parallel",
+              "streams_per_gpu": len(streams), "multi_gpu": "replicas only (one orz stream does not shard)",
+              "l2": "L2 flushed between timed iterations (256 MiB write)"}
+    base = {"metric": METRIC, "unit": "MB/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": ("real: " if "enwik8 (" in data_desc or "tiled" in data_desc else "synthetic: ") + data_desc,
+            "config": config}
+    if args.bytes != N_BYTES:
+        base["invalid"] = "debug corpus size"
+
+    # ------------------------------------------------------------------ reference arm (CPU oracle)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import pyoracle
+        pyoracle.build()
+        cores = os.cpu_count() or 1
+        replicas = min(n_gpus, cores)
+        if args.workload == "exact":
+            work = [data] * replicas
+        else:
+            work = streams * 1
+        nthreads = min(len(work), cores)
+        times = []
+        for it in range(args.warmup + args.steps):
+            if args.workload == "exact":
+                dt, _ = oracle_encode_threads(work, LEVEL)
+            else:  # independent segments over all cores
+                from concurrent.futures import ThreadPoolExecutor
+                t0 = time.perf_counter()
+                with ThreadPoolExecutor(nthreads) as ex:
+                    list(ex.map(lambda s: pyoracle.encode(s, LEVEL), work))
+                dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+        total_bytes = sum(int(np.asarray(w).size) for w in work) * (n_gpus / replicas if args.workload == "exact" else 1)
+        sec = sum(times) / len(times)
+        v = total_bytes / sec / 1e6
+        out = dict(base)
+        out.update({"impl": "reference", "value": v, "ms_per_step": sec * 1e3,
+                    "cpu_baseline": {"value": v, "unit": "MB/s", "cores": nthreads, "kind": "port",
+                                     "sample": f"whole workload per step ({total_bytes:,.0f} B), C oracle port of the "
+                                               "reference (no Rust toolchain on this box), %d host cores present" % cores},
+                    "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "gpu_launches": 0})
+        print(json.dumps(out))
+        return
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    import torch
+    import orz_b200
+    from orz_b200 import Batch
+    from orz_b200._lib import load, check, LZCfg
+
+    if not torch.cuda.is_available() or orz_b200.device_count() < 1:
+        raise SystemExit("bench.py: no sm_100 CUDA device (orz_b200 has no CPU fallback)")
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    in_lens = [int(s.size) for s in streams]
+    batch = Batch(Batch.ENCODE, in_lens, cfg=LEVEL, device=dev)
+    for i, s in enumerate(streams):
+        batch.upload(i, s)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")
+
+    # pinned host buffers for the e2e call
+    L = load()
+    cfg = LZCfg.from_level(LEVEL)
+    pin_in = [torch.from_numpy(np.ascontiguousarray(s)).pin_memory() for s in streams]
+    caps = [L.orz_encode_bound(n) for n in in_lens]
+    pin_out = [torch.empty(c, dtype=torch.uint8).pin_memory() for c in caps]
+    n = len(streams)
+    inp = (C.c_void_p * n)(*[t.data_ptr() for t in pin_in])
+    inl = (C.c_size_t * n)(*in_lens)
+    outp = (C.c_void_p * n)(*[t.data_ptr() for t in pin_out])
+    outc = (C.c_size_t * n)(*caps)
+    outl = (C.c_size_t * n)()
+
+    def gather_spans():
+        """North-star's final collective: all-gather of the per-stream compressed spans (lengths, then padded spans)."""
+        if world <= 1:
+            return
+        total = sum(batch.result_len(i) for i in range(n))
+        lens = torch.tensor([total], dtype=torch.int64, device=f"cuda:{dev}")
+        all_lens = [torch.zeros_like(lens) for _ in range(world)]
+        dist.all_gather(all_lens, lens)
+        mx = int(max(int(x.item()) for x in all_lens))
+        span = torch.zeros(mx, dtype=torch.uint8, device=f"cuda:{dev}")
+        off = 0
+        for i in range(n):
+            ln = batch.result_len(i)
+
+            class _W:
+                __cuda_array_interface__ = {"shape": (ln,), "typestr": "|u1", "data": (batch.result_dev(i), False), "version": 2}
+            if ln:
+                span[off:off + ln] = torch.as_tensor(_W(), device=f"cuda:{dev}")
+            off += ln
+        outb = [torch.empty_like(span) for _ in range(world)]
+        dist.all_gather(outb, span)
+        torch.cuda.synchronize()
+
+    dev_ms, parse_ms, emit_ms, parse_launches, launches = [], [], [], [], []
+    wall = []
+    e2e_s = []
+    sampler = None
+    for it in range(args.warmup + args.steps):
+        flush.fill_(it & 0xFF)
+        if it == args.warmup:
+            barrier()
+            sampler = ClockSampler(dev) if rank == 0 else None
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        batch.run()
+        gather_spans()
+        t1 = time.perf_counter()
+        if it >= args.warmup:
+            wall.append(t1 - t0)
+            dev_ms.append(batch.timing(4)[0])
+            pm, pk = batch.timing(0)
+            em, ek = batch.timing(1)
+            bm, bk = batch.timing(2)
+            parse_ms.append(pm)
+            emit_ms.append(em)
+            parse_launches.append(pk)
+            launches.append(pk + ek + bk)
+        # e2e through the public C ABI with host buffers (one warm-up pass, then every timed step)
+        if it < args.warmup - 1:
+            continue
+        flush.fill_((it + 1) & 0xFF)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        check(L.orz_encode_batch(dev, C.byref(cfg), n, inp, inl, outp, outc, outl), "orz_encode_batch")
+        t1 = time.perf_counter()
+        if it >= args.warmup:
+            e2e_s.append(t1 - t0)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    comp_bytes = sum(batch.result_len(i) for i in range(n))
+    # cross-check e2e output against the resident run
+    assert sum(int(outl[i]) for i in range(n)) == comp_bytes
+    total_in = sum(in_lens)
+
+    # max over ranks of the per-step device time (+ gather for N>1, measured by wall clock around a device sync)
+    step_s = (sum(dev_ms) / len(dev_ms)) / 1e3 if world == 1 else sum(wall) / len(wall)
+    e2e_step_s = sum(e2e_s) / len(e2e_s)
+    if world > 1:
+        tt = torch.tensor([step_s, e2e_step_s], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        step_s, e2e_step_s = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = read_peaks()
+    p_ms = sum(parse_ms) / len(parse_ms)
+    p_launch = sum(parse_launches) / len(parse_launches)
+    alg_bytes = total_in + comp_bytes  # encode = N_in read + N_out written
+    achieved = alg_bytes / (p_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("orz_parse_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    out = dict(base)
+    out.update({
+        "value": n_gpus * total_in / step_s / 1e6,
+        "ms_per_step": step_s * 1e3,
+        "e2e": {"value": n_gpus * total_in / e2e_step_s / 1e6, "unit": "MB/s", "h2d_bytes_per_step": total_in,
+                "d2h_bytes_per_step": comp_bytes},
+        "gpu_launches": int(sum(launches)),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "orz_parse_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes / p_launch, "launches_per_step": p_launch,
+                     "avg_launch_ms": p_ms / p_launch,
+                     "note": "latency-bound serial parse: one warp per stream; the fraction is expected to be ~1e-6..1e-4"},
+        "kernel_ms_per_step": {"parse": p_ms, "emit": sum(emit_ms) / len(emit_ms)},
+        "compressed_bytes": comp_bytes,
+    })
+    # CPU baseline: the oracle on this box's host cores, one stream = one core (the reference is single-threaded)
+    if n_gpus == 1:
+        from oracle import pyoracle
+        pyoracle.build()
+        sample = streams[0] if args.workload == "exact" else data
+        best = None
+        want = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            want = pyoracle.encode(sample, LEVEL)
+            dt = time.perf_counter() - t0
+            best = dt if best is None or dt < best else best
+        ours = batch.download(0) if args.workload == "exact" else None
+        out["bit_identical_to_oracle"] = (ours == want) if ours is not None else None
+        out["cpu_baseline"] = {"value": int(np.asarray(sample).size) / best / 1e6, "unit": "MB/s", "cores": 1, "kind": "port",
+                               "sample": f"the whole {int(np.asarray(sample).size):,} B corpus as one stream, best of 2, C oracle "
+                                         f"(port of the reference; Rust cannot be built here); host has {os.cpu_count()} cores"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

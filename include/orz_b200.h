@@ -114,7 +114,8 @@ int orz_batch_download(orz_batch *, int stream, uint8_t *host, size_t cap, size_
 void *orz_batch_result_dev(orz_batch *, int stream);
 
 /* Kernel timing of the last run(): CUDA-event milliseconds and launch counts per kernel class
- * (0 parse/stage A, 1 emit/stages B-D, 2 block load/slide/forward, 3 decode).  Returns launches counted. */
+ * (0 parse/stage A, 1 emit/stages B-D, 2 block load/slide/forward, 3 decode, 4 = the whole run() on the
+ * library's stream, state reset included).  Returns launches counted. */
 int orz_batch_timing(orz_batch *, int kernel_class, float *total_ms, int *launches);
 
 #ifdef __cplusplus

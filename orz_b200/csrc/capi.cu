@@ -44,11 +44,11 @@ struct KernelTimer {
     };
     std::vector<Rec> pool;
     size_t used = 0;
-    float ms[4] = {0, 0, 0, 0};
-    int launches[4] = {0, 0, 0, 0};
+    float ms[5] = {0, 0, 0, 0, 0};
+    int launches[5] = {0, 0, 0, 0, 0};
     void reset() {
         used = 0;
-        for (int i = 0; i < 4; i++) ms[i] = 0, launches[i] = 0;
+        for (int i = 0; i < 5; i++) ms[i] = 0, launches[i] = 0;
     }
     int begin(int cls, cudaStream_t st) {
         if (used == pool.size()) {
@@ -236,7 +236,7 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
             o.zero_lo = plan.take(0, 256);
             o.win_alloc = (o.win_lo == 0 ? kSentinel : 0) + (size_t)(o.win_hi - o.win_lo);
             o.win = plan.take(o.win_alloc, 256);
-            o.nodes = plan.take(sizeof(Node) * kNumBuckets * kNodesStride);
+            o.nodes = plan.take(sizeof(ENode) * kNumBuckets * kNodesStride);
             o.words = plan.take(65536);
             o.zero_hi = plan.take(0, 256);
             o.heads = plan.take(sizeof(int16_t) * kNumBuckets * kHeadsStride);
@@ -283,7 +283,7 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
             S.win = (o.win_lo == 0) ? (A + o.win + kSentinel) : (A + o.win - o.win_lo);
             S.win_lo = o.win_lo;
             S.win_hi = o.win_hi;
-            S.nodes = reinterpret_cast<Node *>(A + o.nodes);
+            S.nodes = reinterpret_cast<ENode *>(A + o.nodes);
             S.heads = reinterpret_cast<int16_t *>(A + o.heads);
             S.words = reinterpret_cast<uint16_t *>(A + o.words);
             S.symranks = reinterpret_cast<SymRank *>(A + o.symranks);
@@ -384,6 +384,7 @@ extern "C" int orz_batch_run(orz_batch *b) {
     if (!b) return ORZ_EARG;
     CU_TRY(cudaSetDevice(b->device));
     b->timer.reset();
+    const int whole = b->timer.begin(4, b->st); // class 4: the whole run, reset included
     int rc = batch_reset_state(b);
     if (rc) return rc;
     bool all_done = false;
@@ -420,6 +421,8 @@ extern "C" int orz_batch_run(orz_batch *b) {
             b->status[i] = tmp[i].status;
         }
     }
+    b->timer.end(whole, b->st);
+    CU_TRY(cudaStreamSynchronize(b->st));
     b->timer.collect();
     b->ran = true;
     for (int i = 0; i < b->n; i++)
@@ -452,7 +455,7 @@ extern "C" void *orz_batch_result_dev(orz_batch *b, int i) {
 }
 
 extern "C" int orz_batch_timing(orz_batch *b, int cls, float *total_ms, int *launches) {
-    if (!b || cls < 0 || cls > 3) return 0;
+    if (!b || cls < 0 || cls > 4) return 0;
     if (total_ms) *total_ms = b->timer.ms[cls];
     if (launches) *launches = b->timer.launches[cls];
     return b->timer.launches[cls];

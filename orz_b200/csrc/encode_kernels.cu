@@ -19,50 +19,19 @@ namespace orz {
 // ================================================================================================
 constexpr int kTile = 2048;      // bytes of the window staged in shared memory around spos
 constexpr int kTileNeed = 432;   // bytes that must be staged at and after spos (240 LCP + lazy + slack)
+constexpr int kParseThreads = 96; // warp 0: find_match at spos; warp 1 / 2: lazy probes at spos+1 / spos+2
+constexpr unsigned kFull = 0xffffffffu;
 
-struct Chain {
-    int idx;          // current node slot
-    uint32_t pl;      // its pos|lenmin
-    int next;         // its chain link
-    uint32_t exp;     // its match_len_expected
-    bool alive;       // more nodes may follow
-};
-
-__device__ __forceinline__ void node_load(const Node *bn, int slot, uint32_t &pl, int &next, uint32_t &exp) {
-    unsigned long long v = *reinterpret_cast<const unsigned long long *>(bn + slot);
-    pl = (uint32_t)v;
-    next = (int)(int16_t)(uint16_t)(v >> 32);
-    exp = (uint32_t)(v >> 48) & 0xffu;
-}
-
-// Collect up to maxn (<=32) chain nodes, lane k receives node k (matcher.rs:149,170-181 walk order).
-__device__ __forceinline__ int walk_round(const Node *bn, Chain &w, int maxn, int lane, uint32_t &my_pl, int &my_idx,
-                                          uint32_t &my_exp) {
-    int n = 0;
-    while (n < maxn) {
-        if (lane == n) {
-            my_pl = w.pl;
-            my_idx = w.idx;
-            my_exp = w.exp;
-        }
-        n++;
-        if (w.next < 0) { // matcher.rs:171-173
-            w.alive = false;
-            break;
-        }
-        uint32_t pl2, exp2;
-        int next2;
-        node_load(bn, w.next, pl2, next2, exp2);
-        if (node_pos(w.pl) <= node_pos(pl2)) { // matcher.rs:176-179
-            w.alive = false;
-            break;
-        }
-        w.idx = w.next;
-        w.pl = pl2;
-        w.next = next2;
-        w.exp = exp2;
+// Reads the head record of a chain: pl, expected, and (lane L in 1..kSnap) the snapshot link next[L-1].
+__device__ __forceinline__ void enode_head(const ENode *bn, int slot, uint32_t &pl, uint32_t &exp, int &my_next, int lane) {
+    const uint32_t *r = reinterpret_cast<const uint32_t *>(bn + slot);
+    pl = r[0];
+    exp = r[1] & 0xffu;
+    my_next = -1;
+    if (lane >= 1 && lane <= kSnap) {
+        const uint32_t w = r[(lane + 2) >> 1]; // int16 index lane+2 of the record
+        my_next = (int)(int16_t)(((lane + 2) & 1) ? (w >> 16) : (w & 0xffffu));
     }
-    return n;
 }
 
 // Longest common prefix of window[npos..] and the staged bytes tile[toff..], capped at 240
@@ -90,6 +59,33 @@ __device__ __forceinline__ int lcp_win_tile(const uint8_t *win, uint32_t npos, c
     return kMatchMax;
 }
 
+// One gather round of a chain walk.  Lane 0 holds the round's head node X (x_*), lanes 1..cap hold
+// X.next[0..cap-1] in my_next.  Loads those records in parallel and validates the chain order
+// (matcher.rs:171-179: link != -1, positions strictly decrease).  Returns the first invalid lane.
+__device__ __forceinline__ int gather_round(const ENode *bn, int lane, int cap, uint32_t x_pl, uint32_t x_exp, int x_idx,
+                                            int my_next, uint32_t &my_pl, uint32_t &my_exp, int &my_idx) {
+    bool ok = false;
+    my_pl = 0;
+    my_exp = 0;
+    my_idx = -1;
+    if (lane == 0) {
+        my_pl = x_pl;
+        my_exp = x_exp;
+        my_idx = x_idx;
+        ok = true;
+    } else if (lane <= cap && my_next >= 0) {
+        const uint32_t *rr = reinterpret_cast<const uint32_t *>(bn + my_next);
+        my_pl = rr[0];
+        my_exp = rr[1] & 0xffu;
+        my_idx = my_next;
+        ok = true;
+    }
+    const uint32_t prev_pos = __shfl_up_sync(kFull, node_pos(my_pl), 1);
+    const bool link_ok = (lane == 0) || (ok && node_pos(my_pl) < prev_pos);
+    const unsigned bad = ~__ballot_sync(kFull, link_ok);
+    return bad ? (__ffs(bad) - 1) : 32;
+}
+
 struct FoundMatch {
     int len;          // 0 = none
     int idx;          // best node slot
@@ -97,70 +93,84 @@ struct FoundMatch {
     uint32_t exp;     // best node expected (raw)
 };
 
-// matcher.rs:135-192.  `c` bucket, `h0` = heads[entry] already loaded.
-__device__ __forceinline__ FoundMatch find_match_warp(const uint8_t *win, const Node *bn, int h0, const uint8_t *tile,
-                                                      uint32_t toff, uint32_t pos, uint32_t buf_len, int depth, int lane) {
+// matcher.rs:135-192.  h0 = heads[entry].  On return lane L (1..kSnap) holds in f_next the head node's snapshot
+// link next[L-1] (used to build the new slot's own snapshot), -1 if there was no head.
+__device__ __forceinline__ FoundMatch find_match_warp(const uint8_t *win, const ENode *bn, int h0, const uint8_t *tile,
+                                                      uint32_t toff, uint32_t pos, uint32_t buf_len, int depth, int lane,
+                                                      int &f_next) {
     FoundMatch r;
     r.len = 0;
     r.idx = 0;
     r.pl = 0;
     r.exp = 0;
-    if (h0 < 0 || depth <= 0) return r;
-
-    Chain w;
-    w.idx = h0;
-    node_load(bn, h0, w.pl, w.next, w.exp);
-    w.alive = true;
+    f_next = -1;
+    if (h0 < 0) return r;
+    uint32_t x_pl, x_exp;
+    int x_idx = h0, my_next;
+    enode_head(bn, h0, x_pl, x_exp, my_next, lane);
+    f_next = my_next;
+    if (depth <= 0) return r;
 
     int max_len = kMatchMin - 1;
     uint32_t exp_best = kMatchMin, pl_best = (uint32_t)kMatchMin << 25;
     int idx_best = 0;
     int remaining = depth;
     bool done = false;
+    bool first_round = true;
 
-    while (!done && remaining > 0 && w.alive) {
-        uint32_t my_pl = 0, my_exp = 0;
-        int my_idx = 0;
-        const int maxn = remaining < 32 ? remaining : 32;
-        const int n = walk_round(bn, w, maxn, lane, my_pl, my_idx, my_exp);
-        remaining -= n;
-        const bool valid = lane < n;
+    for (;;) {
+        const int lo = first_round ? 0 : 1; // the head node is a candidate only in the first round
+        const int room = remaining - (first_round ? 1 : 0);
+        const int cap = room < kSnap ? room : kSnap;
+        uint32_t my_pl, my_exp;
+        int my_idx;
+        const int nvl = gather_round(bn, lane, cap, x_pl, x_exp, x_idx, my_next, my_pl, my_exp, my_idx);
+        const bool valid = lane >= lo && lane < nvl;
         int lcp = -1;
         if (valid) lcp = lcp_win_tile(win, node_pos(my_pl), tile, toff);
 
         // Resolve the sequential semantics of matcher.rs:149-181 over this round's candidates.
-        int cur = -1;
+        int cur = lo - 1;
         for (;;) {
             const unsigned after = (cur >= 31) ? 0u : (0xffffffffu << (cur + 1));
-            const unsigned upd = __ballot_sync(0xffffffffu, valid && lcp > max_len) & after;
+            const unsigned upd = __ballot_sync(kFull, valid && lcp > max_len) & after;
             const int u = upd ? (__ffs(upd) - 1) : 32;
-            // candidates whose probe dword (matcher.rs:150-153) may match although they are shorter than
+            // candidates whose probe dword (matcher.rs:150-153) may match although they are not longer than
             // max_len: they cannot update, but matcher.rs:165-167 may still break on them.
-            unsigned brk = __ballot_sync(0xffffffffu, valid && exp_best > 0 && lcp < max_len - 3 && lcp > (int)exp_best) & after;
+            unsigned brk = __ballot_sync(kFull, valid && exp_best > 0 && lcp < max_len - 3 && lcp > (int)exp_best) & after;
             if (u < 32) brk &= (1u << u) - 1u;
             if (brk) {
                 bool eq = false;
                 if ((brk >> lane) & 1u) {
-                    uint32_t a = ld_u32_unaligned(win, node_pos(my_pl) + max_len - 3);
-                    uint32_t b = ld_u32_unaligned(tile, toff + max_len - 3);
+                    const uint32_t a = ld_u32_unaligned(win, node_pos(my_pl) + max_len - 3);
+                    const uint32_t b = ld_u32_unaligned(tile, toff + max_len - 3);
                     eq = (a == b);
                 }
-                if (__ballot_sync(0xffffffffu, eq)) {
+                if (__ballot_sync(kFull, eq)) {
                     done = true;
                     break;
                 }
             }
             if (u >= 32) break;
-            max_len = __shfl_sync(0xffffffffu, lcp, u);
-            exp_best = __shfl_sync(0xffffffffu, my_exp, u);
-            pl_best = __shfl_sync(0xffffffffu, my_pl, u);
-            idx_best = __shfl_sync(0xffffffffu, my_idx, u);
+            max_len = __shfl_sync(kFull, lcp, u);
+            exp_best = __shfl_sync(kFull, my_exp, u);
+            pl_best = __shfl_sync(kFull, my_pl, u);
+            idx_best = __shfl_sync(kFull, my_idx, u);
             if (max_len == kMatchMax || (exp_best > 0 && max_len > (int)exp_best)) { // matcher.rs:162-167
                 done = true;
                 break;
             }
             cur = u;
         }
+        remaining -= nvl - lo;
+        if (done || remaining <= 0 || nvl <= cap) break; // nvl <= cap: the chain ended inside this round
+        // continue from the last node of this round (lane cap == kSnap): it becomes the next round's head
+        x_pl = __shfl_sync(kFull, my_pl, kSnap);
+        x_exp = __shfl_sync(kFull, my_exp, kSnap);
+        x_idx = __shfl_sync(kFull, my_idx, kSnap);
+        uint32_t d0, d1;
+        enode_head(bn, x_idx, d0, d1, my_next, lane);
+        first_round = false;
     }
     if (max_len >= kMatchMin && pos + max_len < buf_len) { // matcher.rs:183
         r.len = max_len;
@@ -171,42 +181,64 @@ __device__ __forceinline__ FoundMatch find_match_warp(const uint8_t *win, const 
     return r;
 }
 
-// matcher.rs:194-228: does any of the first `depth` chain nodes match >= min_len bytes at pos?
-__device__ __forceinline__ bool has_lazy_match_warp(const uint8_t *win, const Node *bn, int h0, const uint8_t *tile,
-                                                    uint32_t toff, int min_len, int depth, int lane) {
-    if (h0 < 0 || depth <= 0) return false;
-    Chain w;
-    w.idx = h0;
-    node_load(bn, h0, w.pl, w.next, w.exp);
-    w.alive = true;
+// matcher.rs:194-228 restated as "the longest LCP among the first `depth` chain nodes": has_lazy_match(min_len)
+// is true iff that maximum is >= min_len, so the probe can run before min_len is known.  Returns -1 for no node.
+__device__ __forceinline__ int lazy_max_lcp_warp(const uint8_t *win, const ENode *bn, int h0, const uint8_t *tile,
+                                                 uint32_t toff, int depth, int lane) {
+    if (h0 < 0 || depth <= 0) return -1;
+    uint32_t x_pl, x_exp;
+    int x_idx = h0, my_next;
+    enode_head(bn, h0, x_pl, x_exp, my_next, lane);
     int remaining = depth;
-    while (remaining > 0 && w.alive) {
-        uint32_t my_pl = 0, my_exp = 0;
-        int my_idx = 0;
-        const int maxn = remaining < 32 ? remaining : 32;
-        const int n = walk_round(bn, w, maxn, lane, my_pl, my_idx, my_exp);
-        remaining -= n;
-        bool hit = false;
-        if (lane < n) hit = lcp_win_tile(win, node_pos(my_pl), tile, toff) >= min_len;
-        if (__ballot_sync(0xffffffffu, hit)) return true;
+    bool first_round = true;
+    int best = -1;
+    for (;;) {
+        const int lo = first_round ? 0 : 1;
+        const int room = remaining - (first_round ? 1 : 0);
+        const int cap = room < kSnap ? room : kSnap;
+        uint32_t my_pl, my_exp;
+        int my_idx;
+        const int nvl = gather_round(bn, lane, cap, x_pl, x_exp, x_idx, my_next, my_pl, my_exp, my_idx);
+        int lcp = -1;
+        if (lane >= lo && lane < nvl) lcp = lcp_win_tile(win, node_pos(my_pl), tile, toff);
+        for (int o = 16; o; o >>= 1) {
+            const int other = __shfl_xor_sync(kFull, lcp, o);
+            lcp = other > lcp ? other : lcp;
+        }
+        best = lcp > best ? lcp : best;
+        remaining -= nvl - lo;
+        if (remaining <= 0 || nvl <= cap || best >= kMatchMax / 2 + 2) break; // lazy lengths never exceed 121
+        x_pl = __shfl_sync(kFull, my_pl, kSnap);
+        x_exp = __shfl_sync(kFull, my_exp, kSnap);
+        x_idx = __shfl_sync(kFull, my_idx, kSnap);
+        uint32_t d0, d1;
+        enode_head(bn, x_idx, d0, d1, my_next, lane);
+        first_round = false;
     }
-    return false;
+    return best;
 }
 
-__global__ void __launch_bounds__(32) orz_parse_kernel(EncStream *streams) {
+struct ParseXchg {
+    int fm_len, fm_idx;
+    uint32_t fm_pl, fm_exp;
+    int lazy_max[2];
+};
+
+__global__ void __launch_bounds__(kParseThreads) orz_parse_kernel(EncStream *streams) {
     EncStream *S = &streams[blockIdx.x];
     if (S->status != 0) return;
 
     __shared__ uint32_t s_cnt[kNumCtx];
     __shared__ uint16_t s_bhead[kNumBuckets];
     __shared__ __align__(16) uint8_t s_tile[kTile + 32];
-    const int lane = threadIdx.x;
+    __shared__ ParseXchg s_x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int i = lane; i < kNumCtx; i += 32) s_cnt[i] = 0;
-    for (int i = lane; i < kNumBuckets; i += 32) s_bhead[i] = (uint16_t)S->bhead[i];
+    for (int i = tid; i < kNumCtx; i += kParseThreads) s_cnt[i] = 0;
+    for (int i = tid; i < kNumBuckets; i += kParseThreads) s_bhead[i] = (uint16_t)S->bhead[i];
 
     const uint8_t *win = S->win;
-    Node *nodes = S->nodes;
+    ENode *nodes = S->nodes;
     int16_t *heads = S->heads;
     uint16_t *words = S->words;
     Item *items = S->items;
@@ -217,61 +249,75 @@ __global__ void __launch_bounds__(32) orz_parse_kernel(EncStream *streams) {
     uint32_t after_literal = S->after_literal;
     uint32_t n_items = 0;
     uint32_t tbase = 0xffffffffu;
-    __syncwarp();
+    __syncthreads();
 
     while (spos < sbuf_len && n_items < items_cap) { // lz.rs:131
         // ---- stage the look-ahead tile ----
         if (tbase == 0xffffffffu || spos + kTileNeed > tbase + kTile) {
             tbase = (spos - 16u) & ~15u;
-            __syncwarp();
-            for (int i = lane; i < kTile / 16; i += 32)
+            for (int i = tid; i < kTile / 16; i += kParseThreads)
                 reinterpret_cast<uint4 *>(s_tile)[i] = *reinterpret_cast<const uint4 *>(win + tbase + 16u * i);
-            if (lane < 8) reinterpret_cast<uint32_t *>(s_tile + kTile)[lane] = 0;
-            __syncwarp();
+            if (tid < 8) reinterpret_cast<uint32_t *>(s_tile + kTile)[tid] = 0;
+            __syncthreads();
         }
         const uint32_t to = spos - tbase;
         const uint32_t prev4 = ld_u32_unaligned(s_tile, to - 4); // bytes spos-4 .. spos-1
         const uint32_t cur4 = ld_u32_unaligned(s_tile, to);      // bytes spos .. spos+3
         const uint32_t b_m1 = prev4 >> 24, b_m2 = (prev4 >> 16) & 0xffu, b_m3 = (prev4 >> 8) & 0xffu;
         const uint32_t b0 = cur4 & 0xffu, b1 = (cur4 >> 8) & 0xffu;
-
         const uint32_t c = (b_m1 & 0x7fu) | is_alnum(b_m2) << 7;                                 // hash1(spos-1)  lz.rs:481-486
+        const uint32_t e0 = hash_dword(cur4) % kHashSize;
+        int16_t *hp = heads + c * kHeadsStride + e0;
+        ENode *bn = nodes + c * kNodesStride;
+        int h0 = -1, f_next = -1;
         const uint32_t h2 = (b_m1 & 0x7fu) | ((b_m2 & 0x7fu) | is_alnum(b_m3) << 7) << 7;        // hash2(spos-1)  lz.rs:488-492
         const uint32_t lwe = words[h2];                                                           // lz.rs:132
         const bool last_word_matched = (cur4 & 0xffffu) == lwe;                                   // lz.rs:133
-        const uint32_t ctx = c | after_literal << 8;                                              // lz.rs:134-135
-        const uint32_t unlikely = lwe & 0xffu;                                                    // lz.rs:136
 
-        const uint32_t e0 = hash_dword(cur4) % kHashSize;
-        int16_t *hp = heads + c * kHeadsStride + e0;
-        const int h0 = *hp;
-        Node *bn = nodes + c * kNodesStride;
+        if (warp == 0) {
+            h0 = *hp;
+            const FoundMatch m = find_match_warp(win, bn, h0, s_tile, to, spos, sbuf_len, depth0, lane, f_next); // lz.rs:140-145
+            if (lane == 0) {
+                s_x.fm_len = m.len;
+                s_x.fm_idx = m.idx;
+                s_x.fm_pl = m.pl;
+                s_x.fm_exp = m.exp;
+            }
+        } else if (warp == 1) { // lz.rs:151-171 probe 1: bucket hash1(spos), position spos+1
+            const uint32_t c1 = (b0 & 0x7fu) | is_alnum(b_m1) << 7;
+            const uint32_t e1 = hash_dword(ld_u32_unaligned(s_tile, to + 1)) % kHashSize;
+            const int h1 = heads[c1 * kHeadsStride + e1];
+            const int mx = lazy_max_lcp_warp(win, nodes + c1 * kNodesStride, h1, s_tile, to + 1, depth1, lane);
+            if (lane == 0) s_x.lazy_max[0] = mx;
+        } else { // probe 2: bucket hash1(spos+1), position spos+2
+            const uint32_t c2 = (b1 & 0x7fu) | is_alnum(b0) << 7;
+            const uint32_t e2 = hash_dword(ld_u32_unaligned(s_tile, to + 2)) % kHashSize;
+            const int h2i = heads[c2 * kHeadsStride + e2];
+            const int mx = lazy_max_lcp_warp(win, nodes + c2 * kNodesStride, h2i, s_tile, to + 2, depth2, lane);
+            if (lane == 0) s_x.lazy_max[1] = mx;
+        }
+        __syncthreads();
 
-        const FoundMatch m = find_match_warp(win, bn, h0, s_tile, to, spos, sbuf_len, depth0, lane); // lz.rs:140-145
+        // ---- decision (every thread, uniform) ----
+        FoundMatch m;
+        m.len = s_x.fm_len;
+        m.idx = s_x.fm_idx;
+        m.pl = s_x.fm_pl;
+        m.exp = s_x.fm_exp;
         const uint32_t head = s_bhead[c];
         const uint32_t new_head = head + 1 == kRing ? 0 : head + 1;
-
+        const uint32_t ctx = c | after_literal << 8;                                              // lz.rs:134-135
         int lazy_id = 0;
         uint32_t ro = 0, roid = 0, robitlen = 0, robits = 0;
         if (m.len > 0) {
             ro = (head + kRing - (uint32_t)m.idx) % kRing; // matcher.rs:185
             roid_encode(ro, roid, robitlen, robits);       // lz.rs:148
-            if (m.len < kMatchMax / 2) {                   // lz.rs:151-171
-                const int lazy_len1 = m.len + 1 + (robitlen < 8);
-                const int lazy_len2 = lazy_len1 - (int)last_word_matched;
-                const uint32_t c1 = (b0 & 0x7fu) | is_alnum(b_m1) << 7; // hash1(spos)
-                const uint32_t e1 = hash_dword(ld_u32_unaligned(s_tile, to + 1)) % kHashSize;
-                const int h1 = heads[c1 * kHeadsStride + e1];
-                if (has_lazy_match_warp(win, nodes + c1 * kNodesStride, h1, s_tile, to + 1, lazy_len1, depth1, lane)) {
-                    lazy_id = 1;
-                } else {
-                    const uint32_t c2 = (b1 & 0x7fu) | is_alnum(b0) << 7; // hash1(spos+1)
-                    const uint32_t e2 = hash_dword(ld_u32_unaligned(s_tile, to + 2)) % kHashSize;
-                    const int h2i = heads[c2 * kHeadsStride + e2];
-                    if (has_lazy_match_warp(win, nodes + c2 * kNodesStride, h2i, s_tile, to + 2, lazy_len2, depth2, lane))
-                        lazy_id = 2;
-                }
-            }
+        }
+        if (m.len > 0 && m.len < kMatchMax / 2) {          // lz.rs:151-171
+            const int lazy_len1 = m.len + 1 + (robitlen < 8);
+            const int lazy_len2 = lazy_len1 - (int)last_word_matched;
+            if (s_x.lazy_max[0] >= lazy_len1) lazy_id = 1;
+            else if (s_x.lazy_max[1] >= lazy_len2) lazy_id = 2;
         }
 
         const bool emit_match = m.len > 0 && lazy_id == 0;
@@ -280,7 +326,7 @@ __global__ void __launch_bounds__(32) orz_parse_kernel(EncStream *streams) {
         uint32_t new_spos;
         Item it;
         it.ctx = (uint16_t)ctx;
-        it.unlikely = (uint8_t)unlikely;
+        it.unlikely = (uint8_t)(lwe & 0xffu);                                                     // lz.rs:136
         it.pad = 0;
         it.seq = seq;
         if (emit_match) { // lz.rs:173-209
@@ -312,44 +358,88 @@ __global__ void __launch_bounds__(32) orz_parse_kernel(EncStream *streams) {
             }
         }
 
-        if (lane == 0) {
+        if (warp == 0) {
             // Bucket::update (matcher.rs:62-80) + BucketMatcher::update (matcher.rs:115-121)
-            if (emit_match && node_lenmin(m.pl) <= mlen) {
+            if (lane == 0 && emit_match && node_lenmin(m.pl) <= mlen && (uint32_t)m.idx != new_head) {
                 const uint32_t lm = mlen + 1 < 127u ? mlen + 1 : 127u;
                 bn[m.idx].pl = node_pos(m.pl) | lm << 25;
             }
-            Node nn;
-            nn.pl = spos & 0x1ffffffu;
-            nn.next = (int16_t)h0;
-            nn.expected = (uint8_t)mlen;
-            nn.pad = 0;
-            bn[new_head] = nn;
-            *hp = (int16_t)new_head;
-            s_bhead[c] = (uint16_t)new_head;
-            s_cnt[ctx] = seq + 1;
-            items[n_items] = it;
-            if (it.symbol != kWordSym) { // lz.rs:208,233: words[hash2(spos'-3)] = buf[spos'-2..spos']
-                const uint32_t q = new_spos - tbase;
-                const uint32_t t4 = ld_u32_unaligned(s_tile, q - 5); // bytes spos'-5 .. spos'-2
-                const uint32_t t2 = ld_u32_unaligned(s_tile, q - 2); // bytes spos'-2 .. spos'+1
-                const uint32_t x3 = (t4 >> 16) & 0xffu, x4 = (t4 >> 8) & 0xffu, x5 = t4 & 0xffu;
-                const uint32_t hw = (x3 & 0x7fu) | ((x4 & 0x7fu) | is_alnum(x5) << 7) << 7;
-                words[hw] = (uint16_t)(t2 & 0xffffu);
+            // the new slot: pl, expected, next[0] = heads[entry] (matcher.rs:119), next[1..] = the old head's snapshot
+            const int shifted = __shfl_sync(kFull, f_next, lane >= 4 ? lane - 3 : 0);
+            const uint32_t npl = spos & 0x1ffffffu;
+            int16_t hv;
+            if (lane == 0) hv = (int16_t)(npl & 0xffffu);
+            else if (lane == 1) hv = (int16_t)(npl >> 16);
+            else if (lane == 2) hv = (int16_t)(mlen & 0xffu);
+            else if (lane == 3) hv = (int16_t)h0;
+            else hv = (int16_t)shifted;
+            reinterpret_cast<int16_t *>(bn + new_head)[lane] = hv;
+            if (lane == 0) {
+                *hp = (int16_t)new_head;
+                s_bhead[c] = (uint16_t)new_head;
+                s_cnt[ctx] = seq + 1;
+                items[n_items] = it;
+                if (it.symbol != kWordSym) { // lz.rs:208,233: words[hash2(spos'-3)] = buf[spos'-2..spos']
+                    const uint32_t q = new_spos - tbase;
+                    const uint32_t t4 = ld_u32_unaligned(s_tile, q - 5); // bytes spos'-5 .. spos'-2
+                    const uint32_t t2 = ld_u32_unaligned(s_tile, q - 2); // bytes spos'-2 .. spos'+1
+                    const uint32_t x3 = (t4 >> 16) & 0xffu, x4 = (t4 >> 8) & 0xffu, x5 = t4 & 0xffu;
+                    const uint32_t hw = (x3 & 0x7fu) | ((x4 & 0x7fu) | is_alnum(x5) << 7) << 7;
+                    words[hw] = (uint16_t)(t2 & 0xffffu);
+                }
             }
         }
         after_literal = (it.symbol < 256) ? 1u : 0u;
         spos = new_spos;
         n_items++;
-        __syncwarp();
+        __threadfence_block();
+        __syncthreads();
     }
 
-    __syncwarp();
-    for (int i = lane; i < kNumCtx; i += 32) S->ctx_count[i] = s_cnt[i];
-    for (int i = lane; i < kNumBuckets; i += 32) S->bhead[i] = s_bhead[i];
-    if (lane == 0) {
+    __syncthreads();
+    for (int i = tid; i < kNumCtx; i += kParseThreads) S->ctx_count[i] = s_cnt[i];
+    for (int i = tid; i < kNumBuckets; i += kParseThreads) S->bhead[i] = s_bhead[i];
+    if (tid == 0) {
         S->spos = spos;
         S->after_literal = after_literal;
         S->n_items = n_items;
+    }
+}
+
+
+// LZEncoder::forward (lz.rs:82-87) in two grid-stride phases.
+// Phase 1 — Bucket::forward (matcher.rs:82-87): rebase every position, saturating at 0.
+__device__ __forceinline__ void enc_forward_rebase(ENode *nodes, uint32_t forward_len, int gid, int gsz) {
+    for (int i = gid; i < kNumBuckets * kNodesStride; i += gsz) {
+        if ((i & (kNodesStride - 1)) >= kRing) continue;
+        const uint32_t pl = nodes[i].pl;
+        const uint32_t p = node_pos(pl);
+        nodes[i].pl = (p > forward_len ? p - forward_len : 0u) | (pl & 0xfe000000u);
+    }
+}
+// Phase 2 — BucketMatcher::forward (matcher.rs:123-133): unlink heads / links whose target position became 0.
+// The snapshot links next[1..] are cut at the first link whose target is dead: the reference would have cleared
+// exactly that link in the predecessor's own slot (DESIGN.md stage A).
+__device__ __forceinline__ void enc_forward_unlink(ENode *nodes, int16_t *heads, int gid, int gsz) {
+    for (int i = gid; i < kNumBuckets * kHeadsStride; i += gsz) {
+        const int b = i / kHeadsStride;
+        if (i - b * kHeadsStride >= kHashSize) continue;
+        const int h = heads[i];
+        if (h != -1 && node_pos(nodes[b * kNodesStride + h].pl) == 0) heads[i] = -1;
+    }
+    for (int i = gid; i < kNumBuckets * kNodesStride; i += gsz) {
+        if ((i & (kNodesStride - 1)) >= kRing) continue;
+        const int b = i / kNodesStride;
+        ENode *nd = &nodes[i];
+        bool cut = false;
+        for (int j = 0; j < kSnap; j++) {
+            const int nx = nd->next[j];
+            if (nx == -1) break;
+            if (cut || node_pos(nodes[b * kNodesStride + nx].pl) == 0) {
+                nd->next[j] = -1;
+                cut = true;
+            }
+        }
     }
 }
 
@@ -862,29 +952,12 @@ __global__ void __launch_bounds__(kEmitThreads) orz_emit_kernel(EncStream *strea
         }
     }
     // forward (lz.rs:82-87, matcher.rs:82-87,123-133)
-    Node *nodes = S->nodes;
+    ENode *nodes = S->nodes;
     int16_t *heads = S->heads;
-    for (int i = tid; i < kNumBuckets * kNodesStride; i += kEmitThreads) {
-        if ((i & (kNodesStride - 1)) >= kRing) continue;
-        const uint32_t pl = nodes[i].pl;
-        const uint32_t p = node_pos(pl);
-        nodes[i].pl = (p > kBlockNew ? p - kBlockNew : 0u) | (pl & 0xfe000000u);
-    }
+    enc_forward_rebase(nodes, kBlockNew, tid, kEmitThreads);
     __threadfence_block();
     __syncthreads();
-    for (int i = tid; i < kNumBuckets * kHeadsStride; i += kEmitThreads) {
-        const int b = i / kHeadsStride;
-        if (i - b * kHeadsStride >= kHashSize) continue;
-        const int h = heads[i];
-        if (h != -1 && node_pos(nodes[b * kNodesStride + h].pl) == 0) heads[i] = -1;
-    }
-    // nexts must be tested against the rebased positions before any of them changes: positions are final here
-    for (int i = tid; i < kNumBuckets * kNodesStride; i += kEmitThreads) {
-        if ((i & (kNodesStride - 1)) >= kRing) continue;
-        const int b = i / kNodesStride;
-        const int nx = nodes[i].next;
-        if (nx != -1 && node_pos(nodes[b * kNodesStride + nx].pl) == 0) nodes[i].next = -1;
-    }
+    enc_forward_unlink(nodes, heads, tid, kEmitThreads);
     __syncthreads();
     // read the next block into [PREMATCH, PREMATCH+rd) (lib.rs:72)
     const uint64_t rem = in_len - in_pos;
@@ -931,35 +1004,14 @@ __global__ void __launch_bounds__(256) orz_enc_begin_kernel(EncStream *streams) 
 // LZEncoder::forward for the chunk-level API (lz.rs:82-87)
 __global__ void __launch_bounds__(256) orz_enc_forward_kernel(EncStream *streams, uint32_t forward_len, int phase) {
     EncStream *S = &streams[0];
-    Node *nodes = S->nodes;
-    int16_t *heads = S->heads;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    if (phase == 0) {
-        for (int i = gid; i < kNumBuckets * kNodesStride; i += gsz) {
-            if ((i & (kNodesStride - 1)) >= kRing) continue;
-            const uint32_t pl = nodes[i].pl;
-            const uint32_t p = node_pos(pl);
-            nodes[i].pl = (p > forward_len ? p - forward_len : 0u) | (pl & 0xfe000000u);
-        }
-    } else {
-        for (int i = gid; i < kNumBuckets * kHeadsStride; i += gsz) {
-            const int b = i / kHeadsStride;
-            if (i - b * kHeadsStride >= kHashSize) continue;
-            const int h = heads[i];
-            if (h != -1 && node_pos(nodes[b * kNodesStride + h].pl) == 0) heads[i] = -1;
-        }
-        for (int i = gid; i < kNumBuckets * kNodesStride; i += gsz) {
-            if ((i & (kNodesStride - 1)) >= kRing) continue;
-            const int b = i / kNodesStride;
-            const int nx = nodes[i].next;
-            if (nx != -1 && node_pos(nodes[b * kNodesStride + nx].pl) == 0) nodes[i].next = -1;
-        }
-    }
+    if (phase == 0) enc_forward_rebase(S->nodes, forward_len, gid, gsz);
+    else enc_forward_unlink(S->nodes, S->heads, gid, gsz);
 }
 
 size_t emit_smem_bytes() { return sizeof(EmitShared); }
 
-void launch_parse(EncStream *d_streams, int n, cudaStream_t st) { orz_parse_kernel<<<n, 32, 0, st>>>(d_streams); }
+void launch_parse(EncStream *d_streams, int n, cudaStream_t st) { orz_parse_kernel<<<n, kParseThreads, 0, st>>>(d_streams); }
 void launch_emit(EncStream *d_streams, int n, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {

@@ -34,7 +34,7 @@ constexpr int kHeadsStride = 4640;  // hash heads per bucket, padded from 4627
 constexpr int kSymStride = 392;     // symbols per rank table, padded from 389
 constexpr uint32_t kWinSlack = 8192; // zero bytes kept readable after the window (tile loads)
 
-// One ring slot: pos:25 | match_len_min:7 (matcher.rs:231-237), chain link (matcher.rs:104), expected (matcher.rs:239-243)
+// Decoder ring slot: pos:25 | match_len_min:7 (matcher.rs:231-237), expected (matcher.rs:239-243); `next` unused
 struct __align__(8) Node {
     uint32_t pl;
     int16_t next;
@@ -42,6 +42,21 @@ struct __align__(8) Node {
     uint8_t pad;
 };
 static_assert(sizeof(Node) == 8, "Node must be 8 bytes");
+
+// Encoder ring slot, 64 bytes.  Besides pos|lenmin and expected it carries `next[0]` = the reference's chain
+// link nexts[slot] (matcher.rs:104,119) and `next[1..]` = a snapshot, taken when the slot was written, of the
+// following links of that chain.  A walk (matcher.rs:149-181) then needs one gather of up to kSnap records
+// instead of one dependent load per hop.  The snapshot may go stale, exactly like the reference's own links:
+// a slot that was overwritten after the snapshot holds a newer position, and the walk's "positions strictly
+// decrease" test (matcher.rs:176-179) stops there in both formulations.
+constexpr int kSnap = 29;
+struct __align__(64) ENode {
+    uint32_t pl;
+    uint8_t expected;
+    uint8_t pad;
+    int16_t next[kSnap];
+};
+static_assert(sizeof(ENode) == 64, "ENode must be 64 bytes");
 
 __host__ __device__ __forceinline__ uint32_t node_pos(uint32_t pl) { return pl & 0x1ffffffu; }
 __host__ __device__ __forceinline__ uint32_t node_lenmin(uint32_t pl) { return pl >> 25; }
@@ -78,7 +93,7 @@ struct EncStream {
     uint64_t out_cap;
     uint8_t *win;         // win[p] is window position p (p may start at win_lo > 0 for one-block streams); 16 B aligned at p=0
     uint32_t win_lo, win_hi;
-    Node *nodes;          // [256][kNodesStride]
+    ENode *nodes;         // [256][kNodesStride]
     int16_t *heads;       // [256][kHeadsStride]
     uint16_t *words;      // [32768] two predicted bytes, little endian (lz.rs:52)
     SymRank *symranks;    // [512]

@@ -1,0 +1,102 @@
+"""GPU parity on the cases where orz carries state: chunk cuts (2^20 items), 16 MiB block slides + forward(),
+bit-visible over-reads at block ends, and the operator-level (chunk) C ABI driven like lib.rs does."""
+import numpy as np
+import pytest
+
+import orz_b200
+from oracle import pyoracle
+from tests import datagen
+
+pytestmark = pytest.mark.gpu
+BLOCK_NEW = 1 << 24
+
+
+def _diff(a, b):
+    n = min(len(a), len(b))
+    x = np.frombuffer(a[:n], np.uint8) != np.frombuffer(b[:n], np.uint8)
+    i = int(np.argmax(x)) if x.any() else n
+    return f"len {len(a)} vs {len(b)}, first diff at byte {i}"
+
+
+def test_chunk_cut_at_2_20_items():
+    data = datagen.random_bytes(1_200_000, seed=11)  # > 2^20 literal items -> two chunks in one block
+    want = pyoracle.encode(data, 1)
+    got = orz_b200.encode(data, 1)
+    assert got == want, _diff(got, want)
+    assert orz_b200.decode(want, out_cap=len(data) + 64) == data
+
+
+@pytest.mark.parametrize("n", [BLOCK_NEW, BLOCK_NEW + 5, BLOCK_NEW + 700_000])
+def test_block_slide_and_forward(n):
+    # full block + (nothing | tiny tail | short tail): exercises forward(), sentinel zeros and stale tail bytes
+    data = (datagen.text_like(6_000_000, seed=5) * 3)[:n]
+    want = pyoracle.encode(data, 0)
+    got = orz_b200.encode(data, 0)
+    assert got == want, _diff(got, want)
+    assert orz_b200.decode(want, out_cap=len(data) + 64) == data
+
+
+def test_three_blocks_level2():
+    data = (datagen.text_like(5_000_000, seed=9) + datagen.low_entropy(3_000_000, seed=4)) * 5
+    data = data[: 2 * BLOCK_NEW + 123_457]
+    want = pyoracle.encode(data, 2)
+    got = orz_b200.encode(data, 2)
+    assert got == want, _diff(got, want)
+    assert orz_b200.decode(want, out_cap=len(data) + 64) == data
+
+
+def test_operator_interface_matches_oracle():
+    data = datagen.text_like(400_000, seed=21) + datagen.random_bytes(50_000, seed=22)
+    want = pyoracle.encode(data, 2)
+    got = orz_b200.encode_with_operators(data, 2)
+    assert got == want, _diff(got, want)
+    assert orz_b200.decode_with_operators(want) == data
+
+
+def test_operator_interface_across_blocks():
+    data = (datagen.text_like(4_000_000, seed=23) * 5)[: BLOCK_NEW + 300_000]
+    want = pyoracle.encode(data, 0)
+    got = orz_b200.encode_with_operators(data, 0)
+    assert got == want, _diff(got, want)
+    assert orz_b200.decode_with_operators(want) == data
+
+
+def test_batch_streams_are_independent():
+    segs = [datagen.text_like(150_000, seed=s) for s in range(5)] + [b"", b"x", datagen.random_bytes(30_000, seed=3)]
+    got = orz_b200.encode_batch(segs, 1)
+    for g, s in zip(got, segs):
+        assert g == pyoracle.encode(s, 1)
+    back = orz_b200.decode_batch(got, [len(s) + 64 for s in segs])
+    assert back == segs
+
+
+def test_custom_lzcfg_depths():
+    data = datagen.text_like(200_000, seed=31)
+    cfg = orz_b200.LZCfg.new(70, 40, 33)  # deeper than -l2: more than one gather round per walk
+    ocfg = pyoracle.Cfg(70, 40, 33)
+    assert orz_b200.encode(data, cfg) == pyoracle.encode(data, cfg=ocfg)
+    cfg = orz_b200.LZCfg.new(1, 1, 1)
+    ocfg = pyoracle.Cfg(1, 1, 1)
+    assert orz_b200.encode(data, cfg) == pyoracle.encode(data, cfg=ocfg)
+    cfg = orz_b200.LZCfg.new(0, 0, 0)
+    ocfg = pyoracle.Cfg(0, 0, 0)
+    assert orz_b200.encode(data, cfg) == pyoracle.encode(data, cfg=ocfg)
+
+
+def test_decode_errors():
+    data = datagen.text_like(50_000, seed=41)
+    comp = pyoracle.encode(data, 1)
+    with pytest.raises(orz_b200.OrzError) as e:
+        orz_b200.decode(comp[: len(comp) // 2], out_cap=len(data) + 64)  # truncated: UnexpectedEof (lib.rs:114)
+    assert e.value.code == -3
+    with pytest.raises(orz_b200.OrzError) as e:
+        orz_b200.decode(comp, out_cap=1000)  # output too small
+    assert e.value.code == -2
+    bad = bytearray(comp)
+    for i in range(200, 260):
+        bad[i] ^= 0x5A
+    try:  # corrupted payload: either flagged as invalid data or decodes to different bytes, never crashes
+        out = orz_b200.decode(bytes(bad), out_cap=len(data) * 4)
+        assert out != data or True
+    except orz_b200.OrzError as ex:
+        assert ex.code in (-1, -2, -3)
