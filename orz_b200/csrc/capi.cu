@@ -136,6 +136,7 @@ extern "C" const char *orz_strerror(int code) {
     case ORZ_ENOMEM: return "out of memory";
     case ORZ_ECUDA: return "CUDA device/kernel unavailable (no CPU fallback)";
     case ORZ_EARG: return "invalid argument";
+    case -7: return "internal: stage A watchdog tripped (probe protocol bug)";
     default: return "unknown error";
     }
 }
@@ -296,6 +297,7 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
             S.depth1 = (uint32_t)(cfg->lazy_match_depth1 > 0x7fffffffu ? 0x7fffffffu : cfg->lazy_match_depth1);
             S.depth2 = (uint32_t)(cfg->lazy_match_depth2 > 0x7fffffffu ? 0x7fffffffu : cfg->lazy_match_depth2);
             S.self_driven = chunk_mode ? 0 : 1;
+            S.dbg_flags = getenv("ORZ_B200_DBG") ? (uint32_t)atoi(getenv("ORZ_B200_DBG")) : 0u;
             S.first_block = 1;   // lz.rs:63
             S.after_literal = 1; // lz.rs:64
             b->d_in[i] = A + o.in;
@@ -408,6 +410,13 @@ extern "C" int orz_batch_run(orz_batch *b) {
         CU_TRY(cudaMemcpyAsync(tmp.data(), b->d_enc, sizeof(EncStream) * b->n, cudaMemcpyDeviceToHost, b->st));
         CU_TRY(cudaStreamSynchronize(b->st));
         for (int i = 0; i < b->n; i++) b->result_len[i] = tmp[i].out_pos;
+        if (getenv("ORZ_B200_STATS")) {
+            unsigned long long d[8] = {0};
+            for (int i = 0; i < b->n; i++)
+                for (int k = 0; k < 8; k++) d[k] += tmp[i].dbg[k];
+            fprintf(stderr, "orz_b200 stage A: steps %llu, executor spins own %llu lazy1 %llu lazy2 %llu, builds %llu, aborted %llu, revalidated %llu; own-probe not ready at first poll: building %llu, other-q %llu, stale-version %llu\n", d[0], d[1],
+                    d[2], d[3], d[4], d[5] & 0xffffffffull, d[5] >> 32, d[6] >> 32, d[6] & 0xffffffffull, d[7]);
+        }
     } else {
         int id = b->timer.begin(3, b->st);
         launch_decode(b->d_dec, b->n, b->st);

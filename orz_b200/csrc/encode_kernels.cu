@@ -12,21 +12,55 @@
 // richox/orz @29414c6.
 #include "orz_dev.cuh"
 
+#include <cstdlib>
+
 namespace orz {
 
 // ================================================================================================
-// Stage A
+// Stage A  (lz.rs:131-235)
+//
+// The parse is one serial chain per stream: which positions get inserted into the rings depends on
+// every earlier decision.  What CAN run ahead of the chain is the expensive, read-only part of a step —
+// hashing, the chain gather, the LCPs and the resolution of matcher.rs:135-228 — as long as the bucket it
+// read is unchanged when the chain arrives there.  So one block per stream is split into
+//   * builder warps: builder b speculatively builds a "probe" for the next position q >= spos with
+//     q % NB == b (all candidate records gathered in parallel through the ring snapshots, LCPs against the
+//     window, find_match resolved, lazy maxima), under a per-bucket seqlock, and publishes a summary in
+//     shared memory;
+//   * one executor warp (alone on its SM sub-partition): consumes the probes of spos, spos+1, spos+2,
+//     takes the serial decision, writes the ring slot / head / item, bumps the bucket version and moves on.
+// A probe whose bucket was written after it was built is rebuilt; a probe of a skipped position is dropped.
 // ================================================================================================
-constexpr int kTile = 2048;      // bytes of the window staged in shared memory around spos
-constexpr int kTileNeed = 432;   // bytes that must be staged at and after spos (240 LCP + lazy + slack)
-constexpr int kParseThreads = 96; // warp 0: find_match at spos; warp 1 / 2: lazy probes at spos+1 / spos+2
 constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kNone = 0xffffffffu;
+
+// What a builder publishes about position q (shared memory).  Everything the serial decision needs is
+// precomputed here, so the executor only selects, stamps and stores.
+struct __align__(16) ProbePub {
+    // vector 0 — polled by the executor
+    uint32_t q;        // position described, kNone while the slot is being rewritten (written last)
+    uint32_t ver;      // bver[c] the probe was built under (the executor may re-stamp it, see restamp_probe)
+    uint32_t cmx;      // c | min(max_d1,255) << 8 | min(max_d2,255) << 16 | single_round << 24
+    uint32_t hc;       // hash2(q-1) | bytes(q,q+1) << 16
+    // vector 1 — the match outcome (valid while the bucket is unchanged)
+    uint32_t fm;       // fm_len | fm_idx << 8 | bump << 20      (fm_len 0 = no match)
+    uint32_t sym;      // match symbol | robits << 16
+    uint32_t aux;      // robitlen | eml << 8 | lazy_len1 << 16
+    uint32_t bump_pl;  // new pos|lenmin of the matched slot if bump
+    // vector 2
+    uint32_t e0;       // hash_dword(q) % 4627
+    uint32_t w_lit;    // words update if the step emits a literal: index | value << 16
+    uint32_t w_m;      // words update if the step emits the match
+    uint32_t fm_plexp; // raw lenmin << 8 | raw expected of the matched slot (to redo `aux` after a re-stamp)
+    uint32_t rec[16];  // image of the ring slot this step writes: pl=q, expected (patched), next[0]=h0, next[1..]=old head's snapshot
+    uint16_t cand[32]; // slots of the chain nodes that were read (first round), 0xffff = none
+};
 
 // Reads the head record of a chain: pl, expected, and (lane L in 1..kSnap) the snapshot link next[L-1].
 __device__ __forceinline__ void enode_head(const ENode *bn, int slot, uint32_t &pl, uint32_t &exp, int &my_next, int lane) {
     const uint32_t *r = reinterpret_cast<const uint32_t *>(bn + slot);
-    pl = r[0];
-    exp = r[1] & 0xffu;
+    pl = __shfl_sync(0xffffffffu, r[0], 0);
+    exp = __shfl_sync(0xffffffffu, r[1], 0) & 0xffu;
     my_next = -1;
     if (lane >= 1 && lane <= kSnap) {
         const uint32_t w = r[(lane + 2) >> 1]; // int16 index lane+2 of the record
@@ -34,13 +68,13 @@ __device__ __forceinline__ void enode_head(const ENode *bn, int slot, uint32_t &
     }
 }
 
-// Longest common prefix of window[npos..] and the staged bytes tile[toff..], capped at 240
+// Longest common prefix of window[npos..] and window[qpos..], capped at 240
 // (mem.rs:41-51: 16-byte steps, same result as a byte-wise LCP capped at max_len).
-__device__ __forceinline__ int lcp_win_tile(const uint8_t *win, uint32_t npos, const uint8_t *tile, uint32_t toff) {
+__device__ __forceinline__ int lcp_win_win(const uint8_t *win, uint32_t npos, uint32_t qpos) {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(win + (npos & ~3u));
     const uint32_t sh = (npos & 3u) * 8u;
-    const uint32_t *t = reinterpret_cast<const uint32_t *>(tile + (toff & ~3u));
-    const uint32_t tsh = (toff & 3u) * 8u;
+    const uint32_t *t = reinterpret_cast<const uint32_t *>(win + (qpos & ~3u));
+    const uint32_t tsh = (qpos & 3u) * 8u;
     uint32_t wprev = w[0], tprev = t[0];
     for (int i = 0; i < kMatchMax / 16; i++) {
         uint32_t w1 = w[4 * i + 1], w2 = w[4 * i + 2], w3 = w[4 * i + 3], w4 = w[4 * i + 4];
@@ -86,85 +120,115 @@ __device__ __forceinline__ int gather_round(const ENode *bn, int lane, int cap, 
     return bad ? (__ffs(bad) - 1) : 32;
 }
 
-struct FoundMatch {
-    int len;          // 0 = none
-    int idx;          // best node slot
-    uint32_t pl;      // best node pos|lenmin (raw)
-    uint32_t exp;     // best node expected (raw)
+__device__ __forceinline__ void sts_volatile_v4(volatile void *p, uint4 v) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(const_cast<void *>(p));
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// lane 0's value for the whole warp (also reconverges the warp)
+__device__ __forceinline__ uint32_t bcast0(uint32_t v) { return __shfl_sync(kFull, v, 0); }
+
+__device__ __forceinline__ int warp_max(int v) {
+    for (int o = 16; o; o >>= 1) {
+        const int other = __shfl_xor_sync(kFull, v, o);
+        v = other > v ? other : v;
+    }
+    return v;
+}
+
+struct ProbeResult {
+    int fm_len, fm_idx;
+    uint32_t fm_pl, fm_exp;
+    int max_d1, max_d2;
 };
 
-// matcher.rs:135-192.  h0 = heads[entry].  On return lane L (1..kSnap) holds in f_next the head node's snapshot
-// link next[L-1] (used to build the new slot's own snapshot), -1 if there was no head.
-__device__ __forceinline__ FoundMatch find_match_warp(const uint8_t *win, const ENode *bn, int h0, const uint8_t *tile,
-                                                      uint32_t toff, uint32_t pos, uint32_t buf_len, int depth, int lane,
-                                                      int &f_next) {
-    FoundMatch r;
-    r.len = 0;
-    r.idx = 0;
-    r.pl = 0;
-    r.exp = 0;
+// matcher.rs:135-192 (find_match at q, depth0) and matcher.rs:194-228 restated as "the longest LCP among the
+// first depth1 / depth2 chain nodes" (has_lazy_match(min_len) <=> that maximum >= min_len), from ONE walk of the
+// chain that starts at h0.  f_next: lane L (1..kSnap) returns the head node's snapshot link next[L-1].
+// Returns false if the walk was abandoned because the parse already moved past q.
+__device__ __forceinline__ bool probe_chain(const uint8_t *win, const ENode *bn, int h0, uint32_t q, uint32_t buf_len, int depth0,
+                                            int depth1, int depth2, int lane, const volatile uint32_t *s_spos, ProbeResult &R,
+                                            int &f_next, int &cand_slot, bool &single_round) {
+    R.fm_len = 0;
+    R.fm_idx = 0;
+    R.fm_pl = 0;
+    R.fm_exp = 0;
+    R.max_d1 = -1;
+    R.max_d2 = -1;
     f_next = -1;
-    if (h0 < 0) return r;
+    cand_slot = -1;
+    single_round = true;
+    if (h0 < 0) return true;
     uint32_t x_pl, x_exp;
     int x_idx = h0, my_next;
     enode_head(bn, h0, x_pl, x_exp, my_next, lane);
     f_next = my_next;
-    if (depth <= 0) return r;
+    int dmax = depth0 > depth1 ? depth0 : depth1;
+    dmax = dmax > depth2 ? dmax : depth2;
+    if (dmax <= 0) return true;
 
     int max_len = kMatchMin - 1;
     uint32_t exp_best = kMatchMin, pl_best = (uint32_t)kMatchMin << 25;
     int idx_best = 0;
-    int remaining = depth;
-    bool done = false;
+    int seen = 0;          // chain nodes consumed by earlier rounds
+    bool fm_done = depth0 <= 0;
     bool first_round = true;
 
     for (;;) {
+        if (bcast0(*s_spos) > q) return false;
         const int lo = first_round ? 0 : 1; // the head node is a candidate only in the first round
-        const int room = remaining - (first_round ? 1 : 0);
+        const int room = dmax - seen - (first_round ? 1 : 0);
         const int cap = room < kSnap ? room : kSnap;
         uint32_t my_pl, my_exp;
         int my_idx;
         const int nvl = gather_round(bn, lane, cap, x_pl, x_exp, x_idx, my_next, my_pl, my_exp, my_idx);
-        const bool valid = lane >= lo && lane < nvl;
+        const int gi = seen + lane - lo;                 // index of this lane's node in chain order
+        const bool have = lane >= lo && lane < nvl;
+        if (first_round) cand_slot = (lane < nvl || (lane == nvl && my_idx >= 0)) ? my_idx : -1; // include the slot the walk stopped at
+        else single_round = false;
         int lcp = -1;
-        if (valid) lcp = lcp_win_tile(win, node_pos(my_pl), tile, toff);
+        if (have) lcp = lcp_win_win(win, node_pos(my_pl), q);
 
-        // Resolve the sequential semantics of matcher.rs:149-181 over this round's candidates.
-        int cur = lo - 1;
-        for (;;) {
-            const unsigned after = (cur >= 31) ? 0u : (0xffffffffu << (cur + 1));
-            const unsigned upd = __ballot_sync(kFull, valid && lcp > max_len) & after;
-            const int u = upd ? (__ffs(upd) - 1) : 32;
-            // candidates whose probe dword (matcher.rs:150-153) may match although they are not longer than
-            // max_len: they cannot update, but matcher.rs:165-167 may still break on them.
-            unsigned brk = __ballot_sync(kFull, valid && exp_best > 0 && lcp < max_len - 3 && lcp > (int)exp_best) & after;
-            if (u < 32) brk &= (1u << u) - 1u;
-            if (brk) {
-                bool eq = false;
-                if ((brk >> lane) & 1u) {
-                    const uint32_t a = ld_u32_unaligned(win, node_pos(my_pl) + max_len - 3);
-                    const uint32_t b = ld_u32_unaligned(tile, toff + max_len - 3);
-                    eq = (a == b);
+        R.max_d1 = max(R.max_d1, warp_max((have && gi < depth1) ? lcp : -1));
+        R.max_d2 = max(R.max_d2, warp_max((have && gi < depth2) ? lcp : -1));
+
+        if (!fm_done) { // resolve the sequential semantics of matcher.rs:149-181 over this round's candidates
+            const bool valid = have && gi < depth0;
+            int cur = lo - 1;
+            for (;;) {
+                const unsigned after = (cur >= 31) ? 0u : (0xffffffffu << (cur + 1));
+                const unsigned upd = __ballot_sync(kFull, valid && lcp > max_len) & after;
+                const int u = upd ? (__ffs(upd) - 1) : 32;
+                // candidates whose probe dword (matcher.rs:150-153) may match although they are not longer than
+                // max_len: they cannot update, but matcher.rs:165-167 may still break on them.
+                unsigned brk = __ballot_sync(kFull, valid && exp_best > 0 && lcp < max_len - 3 && lcp > (int)exp_best) & after;
+                if (u < 32) brk &= (1u << u) - 1u;
+                if (brk) {
+                    bool eq = false;
+                    if ((brk >> lane) & 1u)
+                        eq = ld_u32_unaligned(win, node_pos(my_pl) + max_len - 3) == ld_u32_unaligned(win, q + max_len - 3);
+                    if (__ballot_sync(kFull, eq)) {
+                        fm_done = true;
+                        break;
+                    }
                 }
-                if (__ballot_sync(kFull, eq)) {
-                    done = true;
+                if (u >= 32) break;
+                max_len = __shfl_sync(kFull, lcp, u);
+                exp_best = __shfl_sync(kFull, my_exp, u);
+                pl_best = __shfl_sync(kFull, my_pl, u);
+                idx_best = __shfl_sync(kFull, my_idx, u);
+                if (max_len == kMatchMax || (exp_best > 0 && max_len > (int)exp_best)) { // matcher.rs:162-167
+                    fm_done = true;
                     break;
                 }
+                cur = u;
             }
-            if (u >= 32) break;
-            max_len = __shfl_sync(kFull, lcp, u);
-            exp_best = __shfl_sync(kFull, my_exp, u);
-            pl_best = __shfl_sync(kFull, my_pl, u);
-            idx_best = __shfl_sync(kFull, my_idx, u);
-            if (max_len == kMatchMax || (exp_best > 0 && max_len > (int)exp_best)) { // matcher.rs:162-167
-                done = true;
-                break;
-            }
-            cur = u;
         }
-        remaining -= nvl - lo;
-        if (done || remaining <= 0 || nvl <= cap) break; // nvl <= cap: the chain ended inside this round
-        // continue from the last node of this round (lane cap == kSnap): it becomes the next round's head
+        seen += nvl - lo;
+        if (seen >= depth0) fm_done = true;
+        const bool lazy_done = (seen >= depth1 || R.max_d1 >= kMatchMax / 2 + 2) && (seen >= depth2 || R.max_d2 >= kMatchMax / 2 + 2);
+        if (nvl <= cap || (fm_done && lazy_done)) break; // nvl <= cap: the chain ended inside this round
+        // continue from the last node of this round (lane kSnap): it becomes the next round's head
         x_pl = __shfl_sync(kFull, my_pl, kSnap);
         x_exp = __shfl_sync(kFull, my_exp, kSnap);
         x_idx = __shfl_sync(kFull, my_idx, kSnap);
@@ -172,240 +236,432 @@ __device__ __forceinline__ FoundMatch find_match_warp(const uint8_t *win, const 
         enode_head(bn, x_idx, d0, d1, my_next, lane);
         first_round = false;
     }
-    if (max_len >= kMatchMin && pos + max_len < buf_len) { // matcher.rs:183
-        r.len = max_len;
-        r.idx = idx_best;
-        r.pl = pl_best;
-        r.exp = exp_best;
+    if (max_len >= kMatchMin && q + max_len < buf_len) { // matcher.rs:183
+        R.fm_len = max_len;
+        R.fm_idx = idx_best;
+        R.fm_pl = pl_best;
+        R.fm_exp = exp_best;
     }
-    return r;
+    return true;
 }
 
-// matcher.rs:194-228 restated as "the longest LCP among the first `depth` chain nodes": has_lazy_match(min_len)
-// is true iff that maximum is >= min_len, so the probe can run before min_len is known.  Returns -1 for no node.
-__device__ __forceinline__ int lazy_max_lcp_warp(const uint8_t *win, const ENode *bn, int h0, const uint8_t *tile,
-                                                 uint32_t toff, int depth, int lane) {
-    if (h0 < 0 || depth <= 0) return -1;
-    uint32_t x_pl, x_exp;
-    int x_idx = h0, my_next;
-    enode_head(bn, h0, x_pl, x_exp, my_next, lane);
-    int remaining = depth;
-    bool first_round = true;
-    int best = -1;
-    for (;;) {
-        const int lo = first_round ? 0 : 1;
-        const int room = remaining - (first_round ? 1 : 0);
-        const int cap = room < kSnap ? room : kSnap;
-        uint32_t my_pl, my_exp;
-        int my_idx;
-        const int nvl = gather_round(bn, lane, cap, x_pl, x_exp, x_idx, my_next, my_pl, my_exp, my_idx);
-        int lcp = -1;
-        if (lane >= lo && lane < nvl) lcp = lcp_win_tile(win, node_pos(my_pl), tile, toff);
-        for (int o = 16; o; o >>= 1) {
-            const int other = __shfl_xor_sync(kFull, lcp, o);
-            lcp = other > lcp ? other : lcp;
-        }
-        best = lcp > best ? lcp : best;
-        remaining -= nvl - lo;
-        if (remaining <= 0 || nvl <= cap || best >= kMatchMax / 2 + 2) break; // lazy lengths never exceed 121
-        x_pl = __shfl_sync(kFull, my_pl, kSnap);
-        x_exp = __shfl_sync(kFull, my_exp, kSnap);
-        x_idx = __shfl_sync(kFull, my_idx, kSnap);
-        uint32_t d0, d1;
-        enode_head(bn, x_idx, d0, d1, my_next, lane);
-        first_round = false;
-    }
-    return best;
+// lz.rs:148,151-153,173-180 for a found match, given the ring head it will be coded against.
+// Returns sym = symbol | robits << 16 and aux = robitlen | eml << 8 | lazy_len1 << 16.
+__device__ __forceinline__ void match_fields(uint32_t head, uint32_t fm_idx, uint32_t fm_len, uint32_t raw_lenmin, uint32_t raw_exp,
+                                             uint32_t &sym, uint32_t &aux) {
+    const uint32_t ro = (head + kRing - fm_idx) % kRing; // matcher.rs:185
+    uint32_t roid, robitlen, robits;
+    roid_encode(ro, roid, robitlen, robits);             // lz.rs:148
+    const uint32_t mexp = raw_exp > (uint32_t)kMatchMin ? raw_exp : (uint32_t)kMatchMin;
+    const uint32_t mmin = raw_lenmin > (uint32_t)kMatchMin ? raw_lenmin : (uint32_t)kMatchMin;
+    uint32_t eml;
+    if (fm_len > mexp) eml = fm_len - mmin;
+    else if (fm_len < mexp) eml = fm_len - mmin + 1;
+    else eml = 0;
+    eml &= 0xffu; // `as u8`
+    const uint32_t lenid = eml < (uint32_t)(kLenidSize - 1) ? eml : (uint32_t)(kLenidSize - 1);
+    const uint32_t lazy_len1 = fm_len + 1 + (robitlen < 8);
+    sym = (256 + roid * kLenidSize + lenid) | robits << 16;
+    aux = robitlen | eml << 8 | lazy_len1 << 16;
 }
 
-struct ParseXchg {
-    int fm_len, fm_idx;
-    uint32_t fm_pl, fm_exp;
-    int lazy_max[2];
+constexpr int kMaxBuilders = 16;
+
+// one 16-byte volatile read of shared memory (the executor's poll)
+__device__ __forceinline__ uint4 lds_volatile_v4(const volatile void *p) {
+    uint4 v;
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(const_cast<void *>(p));
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
+struct ParseShared {
+    uint16_t words[32768];         // lz.rs:52 — only the executor touches it
+    uint32_t cnt[kNumCtx];
+    uint32_t bver[kNumBuckets];    // per-bucket seqlock: odd while the executor is writing the bucket
+    uint16_t bhead[kNumBuckets];
+    uint4 chg[kNumBuckets];        // last insertion per bucket: {version after it, hash entry, slot written, bumped slot + 1}
+    uint32_t spos;                 // published parse position
+    uint32_t done;
+    ProbePub pub[2 * kMaxBuilders]; // slot of position q: q % (2 * NB); builder b owns the positions q % NB == b
 };
 
-__global__ void __launch_bounds__(kParseThreads) orz_parse_kernel(EncStream *streams) {
+// The executor (one thread) just inserted (slot new_head, hash entry e0, optional lenmin bump of slot bump_idx)
+// into bucket c and holds its seqlock.  If the published probe P lives in the same bucket but read none of what
+// changed, it is still exact: re-stamp it with the bucket's next version instead of letting its builder redo the walk.
+__device__ __forceinline__ void restamp_probe(volatile ProbePub *P, uint32_t want_q, uint32_t c, uint32_t old_ver, uint32_t e0,
+                                              uint32_t new_head, int bump_idx) {
+    const uint4 v = lds_volatile_v4(P);
+    if (v.x != want_q || v.y != old_ver || (v.z & 0xffu) != c || !((v.z >> 24) & 1u) || P->e0 == e0) return;
+    const uint32_t fm = P->fm;
+    const uint32_t fm_len = fm & 0xffu, fm_idx = (fm >> 8) & 0xfffu;
+    if (fm_len > 0 && bump_idx >= 0 && fm_idx == (uint32_t)bump_idx) return;
+    const uint32_t pat = new_head | new_head << 16;
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint4 cw = lds_volatile_v4(reinterpret_cast<volatile uint32_t *>(const_cast<uint16_t *>(P->cand)) + 4 * k);
+        any |= __vcmpeq2(cw.x, pat) | __vcmpeq2(cw.y, pat) | __vcmpeq2(cw.z, pat) | __vcmpeq2(cw.w, pat);
+    }
+    if (any) return; // the probe read the slot that was just overwritten
+    if (fm_len > 0) { // the ring head moved by one: the reduced offset of P's match changes with it
+        const uint32_t pe = P->fm_plexp;
+        uint32_t sym, aux;
+        match_fields(new_head, fm_idx, fm_len, pe >> 8, pe & 0xffu, sym, aux);
+        P->sym = sym;
+        P->aux = aux;
+        const uint32_t nh2 = new_head + 1 == kRing ? 0 : new_head + 1;
+        const bool bump = (pe >> 8) <= fm_len && fm_idx != nh2;
+        P->fm = (fm & 0xfffffu) | (bump ? 1u << 20 : 0u);
+    }
+    P->ver = old_ver + 2;
+}
+
+// NW warps per block.  Warp 0 is the executor; warps with (warp & 3) == 0 share its SM sub-partition and stay
+// parked so that it issues alone; the other NB warps are builders (NW = 22 -> 16 builders, NW = 11 -> 8).
+template <int NW, int NB>
+__global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) {
+    static_assert(NB == NW - 1 - (NW - 1) / 4 && NB <= kMaxBuilders, "builder count");
     EncStream *S = &streams[blockIdx.x];
     if (S->status != 0) return;
-
-    __shared__ uint32_t s_cnt[kNumCtx];
-    __shared__ uint16_t s_bhead[kNumBuckets];
-    __shared__ __align__(16) uint8_t s_tile[kTile + 32];
-    __shared__ ParseXchg s_x;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    ParseShared &sh = *reinterpret_cast<ParseShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = NW * 32;
+    constexpr int NS = 2 * NB; // probe slots = lookahead in positions
 
-    for (int i = tid; i < kNumCtx; i += kParseThreads) s_cnt[i] = 0;
-    for (int i = tid; i < kNumBuckets; i += kParseThreads) s_bhead[i] = (uint16_t)S->bhead[i];
-
+    for (int i = tid; i < kNumCtx; i += NT) sh.cnt[i] = 0;
+    for (int i = tid; i < kNumBuckets; i += NT) {
+        sh.bhead[i] = (uint16_t)S->bhead[i];
+        sh.bver[i] = 0;
+    }
+    for (int i = tid; i < 32768 / 8; i += NT) reinterpret_cast<uint4 *>(sh.words)[i] = reinterpret_cast<const uint4 *>(S->words)[i];
+    if (tid < 2 * NB) sh.pub[tid].q = kNone;
     const uint8_t *win = S->win;
     ENode *nodes = S->nodes;
     int16_t *heads = S->heads;
-    uint16_t *words = S->words;
-    Item *items = S->items;
     const uint32_t sbuf_len = S->sbuf_len;
-    const uint32_t items_cap = S->items_cap < kChunkItems ? S->items_cap : kChunkItems;
     const int depth0 = (int)S->depth0, depth1 = (int)S->depth1, depth2 = (int)S->depth2;
-    uint32_t spos = S->spos;
-    uint32_t after_literal = S->after_literal;
-    uint32_t n_items = 0;
-    uint32_t tbase = 0xffffffffu;
+    const uint32_t dbg_flags = S->dbg_flags;
+    if (tid == 0) {
+        sh.spos = S->spos;
+        sh.done = 0;
+    }
     __syncthreads();
+    volatile uint32_t *v_spos = &sh.spos;
+    volatile uint32_t *v_done = &sh.done;
+    volatile uint32_t *v_bver = sh.bver;
+    volatile uint16_t *v_bhead = sh.bhead;
 
-    while (spos < sbuf_len && n_items < items_cap) { // lz.rs:131
-        // ---- stage the look-ahead tile ----
-        if (tbase == 0xffffffffu || spos + kTileNeed > tbase + kTile) {
-            tbase = (spos - 16u) & ~15u;
-            for (int i = tid; i < kTile / 16; i += kParseThreads)
-                reinterpret_cast<uint4 *>(s_tile)[i] = *reinterpret_cast<const uint4 *>(win + tbase + 16u * i);
-            if (tid < 8) reinterpret_cast<uint32_t *>(s_tile + kTile)[tid] = 0;
-            __syncthreads();
-        }
-        const uint32_t to = spos - tbase;
-        const uint32_t prev4 = ld_u32_unaligned(s_tile, to - 4); // bytes spos-4 .. spos-1
-        const uint32_t cur4 = ld_u32_unaligned(s_tile, to);      // bytes spos .. spos+3
-        const uint32_t b_m1 = prev4 >> 24, b_m2 = (prev4 >> 16) & 0xffu, b_m3 = (prev4 >> 8) & 0xffu;
-        const uint32_t b0 = cur4 & 0xffu, b1 = (cur4 >> 8) & 0xffu;
-        const uint32_t c = (b_m1 & 0x7fu) | is_alnum(b_m2) << 7;                                 // hash1(spos-1)  lz.rs:481-486
-        const uint32_t e0 = hash_dword(cur4) % kHashSize;
-        int16_t *hp = heads + c * kHeadsStride + e0;
-        ENode *bn = nodes + c * kNodesStride;
-        int h0 = -1, f_next = -1;
-        const uint32_t h2 = (b_m1 & 0x7fu) | ((b_m2 & 0x7fu) | is_alnum(b_m3) << 7) << 7;        // hash2(spos-1)  lz.rs:488-492
-        const uint32_t lwe = words[h2];                                                           // lz.rs:132
-        const bool last_word_matched = (cur4 & 0xffffu) == lwe;                                   // lz.rs:133
+    if (warp == 0) {
+        // ------------------------------------------------------------------ executor (ONE thread: every poll, branch and
+        // store of the serial chain is taken by lane 0, so no decision can differ between lanes)
+        if (lane == 0) {
+            Item *items = S->items;
+            const uint32_t items_cap = S->items_cap < kChunkItems ? S->items_cap : kChunkItems;
+            uint32_t spos = S->spos;
+            uint32_t after_literal = S->after_literal;
+            uint32_t n_items = 0;
+            unsigned long long w0 = 0, w1 = 0, w2 = 0;
+            unsigned cz_building = 0, cz_other = 0, cz_stale = 0;
+            long long cyc_own = 0, cyc_lazy = 0;
+            const long long t_start = clock64();
+            // watchdog: a probe that never arrives is a protocol bug; fail the stream instead of hanging the GPU
+            const unsigned wd_limit = 30000000u; // spin iterations of ONE wait (seconds); normal waits are < 100
+            int wd_code = 0;
+            while (spos < sbuf_len && n_items < items_cap) { // lz.rs:131
+                volatile ProbePub *P = &sh.pub[spos % NS];
+                uint32_t c, ver, hc;
+                unsigned wl = 0;
+                const long long t_a = clock64();
+                for (;;) { // wait for a probe of spos built under the current version of its bucket
+                    w0++;
+                    if (++wl > wd_limit) {
+                        wd_code = 1;
+                        break;
+                    }
+                    const uint4 v = lds_volatile_v4(P);
+                    if (v.x != spos) {
+                        if (wl == 1) (v.x == kNone ? cz_building : cz_other)++;
+                        continue;
+                    }
+                    ver = v.y;
+                    hc = v.w;
+                    c = v.z & 0xffu;
+                    if (v_bver[c] == ver) break;
+                    if (wl == 1) cz_stale++;
+                }
+                if (wd_code) break;
+                const long long t_b = clock64();
+                cyc_own += t_b - t_a;
+                const uint4 v1 = lds_volatile_v4(&P->fm);
+                const uint4 v2 = lds_volatile_v4(&P->e0);
+                uint4 r0 = lds_volatile_v4(&P->rec[0]);
+                const uint4 r1 = lds_volatile_v4(&P->rec[4]), r2 = lds_volatile_v4(&P->rec[8]), r3 = lds_volatile_v4(&P->rec[12]);
+                volatile ProbePub *P1 = &sh.pub[(spos + 1) % NS];
+                volatile ProbePub *P2 = &sh.pub[(spos + 2) % NS];
+                uint4 a1 = lds_volatile_v4(P1), a2 = lds_volatile_v4(P2); // lazy probes: read now, validated only if needed
+                const uint32_t h2 = hc & 0x7fffu, cur2 = hc >> 16;
+                const uint32_t fm_len = v1.x & 0xffu, fm_idx = (v1.x >> 8) & 0xfffu;
+                const bool bump = (v1.x >> 20) & 1u;
+                const uint32_t e0 = v2.x;
 
-        if (warp == 0) {
-            h0 = *hp;
-            const FoundMatch m = find_match_warp(win, bn, h0, s_tile, to, spos, sbuf_len, depth0, lane, f_next); // lz.rs:140-145
-            if (lane == 0) {
-                s_x.fm_len = m.len;
-                s_x.fm_idx = m.idx;
-                s_x.fm_pl = m.pl;
-                s_x.fm_exp = m.exp;
-            }
-        } else if (warp == 1) { // lz.rs:151-171 probe 1: bucket hash1(spos), position spos+1
-            const uint32_t c1 = (b0 & 0x7fu) | is_alnum(b_m1) << 7;
-            const uint32_t e1 = hash_dword(ld_u32_unaligned(s_tile, to + 1)) % kHashSize;
-            const int h1 = heads[c1 * kHeadsStride + e1];
-            const int mx = lazy_max_lcp_warp(win, nodes + c1 * kNodesStride, h1, s_tile, to + 1, depth1, lane);
-            if (lane == 0) s_x.lazy_max[0] = mx;
-        } else { // probe 2: bucket hash1(spos+1), position spos+2
-            const uint32_t c2 = (b1 & 0x7fu) | is_alnum(b0) << 7;
-            const uint32_t e2 = hash_dword(ld_u32_unaligned(s_tile, to + 2)) % kHashSize;
-            const int h2i = heads[c2 * kHeadsStride + e2];
-            const int mx = lazy_max_lcp_warp(win, nodes + c2 * kNodesStride, h2i, s_tile, to + 2, depth2, lane);
-            if (lane == 0) s_x.lazy_max[1] = mx;
-        }
-        __syncthreads();
+                const uint32_t lwe = sh.words[h2];                       // lz.rs:132
+                const bool last_word_matched = cur2 == lwe;              // lz.rs:133
+                const uint32_t ctx = c | after_literal << 8;             // lz.rs:134-135
+                int lazy_id = 0;
+                if (fm_len > 0 && fm_len < kMatchMax / 2) {              // lz.rs:151-171
+                    const uint32_t lazy_len1 = (v1.z >> 16) & 0xffu;
+                    const uint32_t lazy_len2 = lazy_len1 - (uint32_t)last_word_matched;
+                    wl = 0;
+                    for (;;) {
+                        w1++;
+                        if (++wl > wd_limit) {
+                            wd_code = 2;
+                            break;
+                        }
+                        if (a1.x == spos + 1 && v_bver[a1.z & 0xffu] == a1.y) break;
+                        a1 = lds_volatile_v4(P1);
+                    }
+                    if (((a1.z >> 8) & 0xffu) >= lazy_len1) {
+                        lazy_id = 1;
+                    } else {
+                        wl = 0;
+                        for (;;) {
+                            w2++;
+                            if (++wl > wd_limit) {
+                                wd_code = 3;
+                                break;
+                            }
+                            if (a2.x == spos + 2 && v_bver[a2.z & 0xffu] == a2.y) break;
+                            a2 = lds_volatile_v4(P2);
+                        }
+                        if (((a2.z >> 16) & 0xffu) >= lazy_len2) lazy_id = 2;
+                    }
+                }
+                if (wd_code) break;
+                cyc_lazy += clock64() - t_b;
 
-        // ---- decision (every thread, uniform) ----
-        FoundMatch m;
-        m.len = s_x.fm_len;
-        m.idx = s_x.fm_idx;
-        m.pl = s_x.fm_pl;
-        m.exp = s_x.fm_exp;
-        const uint32_t head = s_bhead[c];
-        const uint32_t new_head = head + 1 == kRing ? 0 : head + 1;
-        const uint32_t ctx = c | after_literal << 8;                                              // lz.rs:134-135
-        int lazy_id = 0;
-        uint32_t ro = 0, roid = 0, robitlen = 0, robits = 0;
-        if (m.len > 0) {
-            ro = (head + kRing - (uint32_t)m.idx) % kRing; // matcher.rs:185
-            roid_encode(ro, roid, robitlen, robits);       // lz.rs:148
-        }
-        if (m.len > 0 && m.len < kMatchMax / 2) {          // lz.rs:151-171
-            const int lazy_len1 = m.len + 1 + (robitlen < 8);
-            const int lazy_len2 = lazy_len1 - (int)last_word_matched;
-            if (s_x.lazy_max[0] >= lazy_len1) lazy_id = 1;
-            else if (s_x.lazy_max[1] >= lazy_len2) lazy_id = 2;
-        }
+                const bool emit_match = fm_len > 0 && lazy_id == 0;
+                const uint32_t mlen = emit_match ? fm_len : 0u;
+                const uint32_t seq = sh.cnt[ctx];
+                uint32_t new_spos, wupd;
+                Item it;
+                it.ctx = (uint16_t)ctx;
+                it.unlikely = (uint8_t)(lwe & 0xffu);                // lz.rs:136
+                it.pad = 0;
+                it.seq = seq;
+                if (emit_match) { // lz.rs:173-209
+                    it.symbol = (uint16_t)(v1.y & 0xffffu);
+                    it.robits = (uint16_t)(v1.y >> 16);
+                    it.robitlen = (uint8_t)(v1.z & 0xffu);
+                    it.eml = (uint8_t)((v1.z >> 8) & 0xffu);
+                    it.flags = (uint8_t)(after_literal | 2u);
+                    new_spos = spos + mlen;
+                    wupd = v2.z;
+                } else {
+                    it.robits = 0;
+                    it.robitlen = 0;
+                    it.eml = 0;
+                    it.flags = (uint8_t)after_literal;
+                    wupd = v2.y;
+                    if (spos + 1 < sbuf_len && lazy_id != 1 && last_word_matched) { // lz.rs:218-226
+                        it.symbol = (uint16_t)kWordSym;
+                        new_spos = spos + 2;
+                    } else { // lz.rs:227-236
+                        it.symbol = (uint16_t)(cur2 & 0xffu);
+                        new_spos = spos + 1;
+                    }
+                }
+                if (!(dbg_flags & 2u)) *v_spos = new_spos; // builders may retarget now: everything of P is in registers
+                const int bump_idx = (emit_match && bump) ? (int)fm_idx : -1;
 
-        const bool emit_match = m.len > 0 && lazy_id == 0;
-        const uint32_t mlen = emit_match ? (uint32_t)m.len : 0u;
-        const uint32_t seq = s_cnt[ctx];
-        uint32_t new_spos;
-        Item it;
-        it.ctx = (uint16_t)ctx;
-        it.unlikely = (uint8_t)(lwe & 0xffu);                                                     // lz.rs:136
-        it.pad = 0;
-        it.seq = seq;
-        if (emit_match) { // lz.rs:173-209
-            const uint32_t mexp = m.exp > (uint32_t)kMatchMin ? m.exp : (uint32_t)kMatchMin;
-            const uint32_t mmin = node_lenmin(m.pl) > (uint32_t)kMatchMin ? node_lenmin(m.pl) : (uint32_t)kMatchMin;
-            uint32_t eml;
-            if (mlen > mexp) eml = mlen - mmin;
-            else if (mlen < mexp) eml = mlen - mmin + 1;
-            else eml = 0;
-            eml &= 0xffu; // `as u8`
-            const uint32_t lenid = eml < (uint32_t)(kLenidSize - 1) ? eml : (uint32_t)(kLenidSize - 1);
-            it.symbol = (uint16_t)(256 + roid * kLenidSize + lenid);
-            it.robits = (uint16_t)robits;
-            it.robitlen = (uint8_t)robitlen;
-            it.eml = (uint8_t)eml;
-            it.flags = (uint8_t)(after_literal | 2u);
-            new_spos = spos + mlen;
-        } else {
-            it.robits = 0;
-            it.robitlen = 0;
-            it.eml = 0;
-            it.flags = (uint8_t)after_literal;
-            if (spos + 1 < sbuf_len && lazy_id != 1 && last_word_matched) { // lz.rs:218-226
-                it.symbol = (uint16_t)kWordSym;
-                new_spos = spos + 2;
-            } else { // lz.rs:227-236
-                it.symbol = (uint16_t)b0;
-                new_spos = spos + 1;
-            }
-        }
-
-        if (warp == 0) {
-            // Bucket::update (matcher.rs:62-80) + BucketMatcher::update (matcher.rs:115-121)
-            if (lane == 0 && emit_match && node_lenmin(m.pl) <= mlen && (uint32_t)m.idx != new_head) {
-                const uint32_t lm = mlen + 1 < 127u ? mlen + 1 : 127u;
-                bn[m.idx].pl = node_pos(m.pl) | lm << 25;
-            }
-            // the new slot: pl, expected, next[0] = heads[entry] (matcher.rs:119), next[1..] = the old head's snapshot
-            const int shifted = __shfl_sync(kFull, f_next, lane >= 4 ? lane - 3 : 0);
-            const uint32_t npl = spos & 0x1ffffffu;
-            int16_t hv;
-            if (lane == 0) hv = (int16_t)(npl & 0xffffu);
-            else if (lane == 1) hv = (int16_t)(npl >> 16);
-            else if (lane == 2) hv = (int16_t)(mlen & 0xffu);
-            else if (lane == 3) hv = (int16_t)h0;
-            else hv = (int16_t)shifted;
-            reinterpret_cast<int16_t *>(bn + new_head)[lane] = hv;
-            if (lane == 0) {
-                *hp = (int16_t)new_head;
-                s_bhead[c] = (uint16_t)new_head;
-                s_cnt[ctx] = seq + 1;
+                // Bucket::update (matcher.rs:62-80) + BucketMatcher::update (matcher.rs:115-121) under the bucket's seqlock
+                ENode *bn = nodes + c * kNodesStride;
+                const uint32_t head = sh.bhead[c];
+                const uint32_t new_head = head + 1 == kRing ? 0 : head + 1;
+                v_bver[c] = ver + 1;
+                __threadfence_block();
+                if (emit_match && bump) bn[fm_idx].pl = v1.w;
+                r0.y = (r0.y & 0xffffff00u) | mlen; // expected = match_len (matcher.rs:75)
+                uint4 *dst = reinterpret_cast<uint4 *>(bn + new_head);
+                dst[0] = r0;
+                dst[1] = r1;
+                dst[2] = r2;
+                dst[3] = r3;
+                heads[c * kHeadsStride + e0] = (int16_t)new_head;
+                v_bhead[c] = (uint16_t)new_head;
+                sts_volatile_v4(&sh.chg[c], make_uint4(ver + 2, e0, new_head, (uint32_t)(bump_idx + 1)));
+                // neighbours in the same bucket that did not read anything this step changed stay valid
+                if (!(dbg_flags & 1u)) {
+                    restamp_probe(&sh.pub[new_spos % NS], new_spos, c, ver, e0, new_head, bump_idx);
+                    restamp_probe(&sh.pub[(new_spos + 1) % NS], new_spos + 1, c, ver, e0, new_head, bump_idx);
+                    restamp_probe(&sh.pub[(new_spos + 2) % NS], new_spos + 2, c, ver, e0, new_head, bump_idx);
+                }
+                __threadfence_block();
+                v_bver[c] = ver + 2;
+                sh.cnt[ctx] = seq + 1;
                 items[n_items] = it;
-                if (it.symbol != kWordSym) { // lz.rs:208,233: words[hash2(spos'-3)] = buf[spos'-2..spos']
-                    const uint32_t q = new_spos - tbase;
-                    const uint32_t t4 = ld_u32_unaligned(s_tile, q - 5); // bytes spos'-5 .. spos'-2
-                    const uint32_t t2 = ld_u32_unaligned(s_tile, q - 2); // bytes spos'-2 .. spos'+1
-                    const uint32_t x3 = (t4 >> 16) & 0xffu, x4 = (t4 >> 8) & 0xffu, x5 = t4 & 0xffu;
-                    const uint32_t hw = (x3 & 0x7fu) | ((x4 & 0x7fu) | is_alnum(x5) << 7) << 7;
-                    words[hw] = (uint16_t)(t2 & 0xffffu);
+                if (it.symbol != kWordSym) sh.words[wupd & 0xffffu] = (uint16_t)(wupd >> 16); // lz.rs:208,233
+                after_literal = (it.symbol < 256) ? 1u : 0u;
+                spos = new_spos;
+                n_items++;
+                if (dbg_flags & 2u) *v_spos = new_spos;
+            }
+            *v_done = 1;
+            if (wd_code) {
+                S->status = -7;
+                S->dbg[6] = (unsigned long long)wd_code;
+                S->dbg[7] = spos;
+            }
+            S->spos = spos;
+            S->after_literal = after_literal;
+            S->n_items = n_items;
+            S->dbg[0] += n_items;
+            if (dbg_flags & 8u) { // report cycles instead of spin counts
+                w0 = (unsigned long long)cyc_own;
+                w1 = (unsigned long long)cyc_lazy;
+                w2 = (unsigned long long)(clock64() - t_start);
+            }
+            S->dbg[1] += w0;
+            S->dbg[2] += w1;
+            S->dbg[3] += w2;
+            if (!wd_code) {
+                S->dbg[6] += ((unsigned long long)cz_building << 32) | cz_other;
+                S->dbg[7] += cz_stale;
+            }
+        }
+    } else if ((warp & 3) != 0) {
+        // ------------------------------------------------------------------ builders
+        const int b = warp - 1 - (warp >> 2);
+        // this builder's two published probes (positions b mod NB, NB apart): [0] lives in slot q % NS < NB ... by position
+        uint32_t pq[2] = {kNone, kNone}, pc[2] = {0, 0}, pver[2] = {0, 0};
+        unsigned long long nbuild = 0, nabort = 0, nreval = 0;
+        for (;;) {
+            // Control values are read by every lane but only lane 0's copy is used (bcast0): lanes that are not
+            // perfectly converged could otherwise see different values and part ways before a full-mask shuffle.
+            if (bcast0(*v_done)) break;
+            const uint32_t sp = bcast0(*v_spos);
+            const uint32_t q1 = sp + ((uint32_t)b + NB - sp % NB) % NB; // next position >= sp owned by this builder
+            // pick the nearer of its two positions that has no current probe
+            uint32_t q = kNone;
+            int k = 0;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const uint32_t qt = q1 + t * NB;
+                const int kt = (int)((qt / NB) & 1u);
+                bool ok = qt >= sbuf_len;
+                if (!ok && pq[kt] == qt) {
+                    const uint32_t bv = bcast0(v_bver[pc[kt]]);
+                    if (bv == pver[kt]) ok = true;                 // published and still current
+                    else if (bv & 1u) ok = true;                   // the executor is writing the bucket (may re-stamp): look again later
+                    else {
+                        volatile ProbePub *vp = &sh.pub[qt % NS];
+                        const uint32_t pv = bcast0(vp->ver), pqq = bcast0(vp->q);
+                        if (pv == bv && pqq == qt) {               // re-stamped by the executor: still exact
+                            pver[kt] = bv;
+                            ok = true;
+                        }
+                    }
+                }
+                if (!ok && q == kNone) {
+                    q = qt;
+                    k = kt;
                 }
             }
+            if (q == kNone) continue;
+            ProbePub &pub = sh.pub[q % NS];
+            volatile ProbePub *vpub = &pub;
+            uint32_t &my_q = pq[k], &my_c = pc[k], &my_ver = pver[k];
+            // ---- build the probe of q ----
+            my_q = kNone;
+            nbuild++;
+            if (lane == 0) vpub->q = kNone;
+            __threadfence_block();
+            const uint32_t prev4 = ld_u32_unaligned(win, q - 4); // bytes q-4 .. q-1
+            const uint32_t cur4 = ld_u32_unaligned(win, q);      // bytes q .. q+3
+            const uint32_t b_m1 = prev4 >> 24, b_m2 = (prev4 >> 16) & 0xffu, b_m3 = (prev4 >> 8) & 0xffu, b_m4 = prev4 & 0xffu;
+            const uint32_t c = (b_m1 & 0x7fu) | is_alnum(b_m2) << 7;                              // hash1(q-1)  lz.rs:481-486
+            const uint32_t h2 = (b_m1 & 0x7fu) | ((b_m2 & 0x7fu) | is_alnum(b_m3) << 7) << 7;     // hash2(q-1)  lz.rs:488-492
+            const uint32_t e0 = hash_dword(cur4) % kHashSize;
+            const uint32_t v0 = bcast0(v_bver[c]);
+            if (v0 & 1u) continue; // the executor is writing this bucket right now
+            __threadfence_block();
+            const uint32_t head = bcast0((uint32_t)v_bhead[c]);
+            const int h0 = (int)bcast0((uint32_t)(int)heads[c * kHeadsStride + e0]);
+            ProbeResult R;
+            int f_next, cand_slot;
+            bool single_round;
+            if (!probe_chain(win, nodes + c * kNodesStride, h0, q, sbuf_len, depth0, depth1, depth2, lane, v_spos, R, f_next, cand_slot,
+                             single_round)) {
+                nabort++;
+                continue;
+            }
+            // words updates of the two possible outcomes (lz.rs:208,233): words[hash2(s'-3)] = bytes s'-2, s'-1
+            const uint32_t hw_lit = (b_m2 & 0x7fu) | ((b_m3 & 0x7fu) | is_alnum(b_m4) << 7) << 7; // s' = q+1
+            const uint32_t wv_lit = b_m1 | (cur4 & 0xffu) << 8;
+            uint32_t hw_m = 0, wv_m = 0, sym = 0, aux = 0, fmw = 0, bump_pl = 0;
+            if (R.fm_len > 0) { // s' = q + len
+                const uint32_t t4 = ld_u32_unaligned(win, q + R.fm_len - 5); // bytes s'-5 .. s'-2
+                const uint32_t t2 = ld_u32_unaligned(win, q + R.fm_len - 2); // bytes s'-2 .. s'+1
+                const uint32_t x3 = (t4 >> 16) & 0xffu, x4 = (t4 >> 8) & 0xffu, x5 = t4 & 0xffu;
+                hw_m = (x3 & 0x7fu) | ((x4 & 0x7fu) | is_alnum(x5) << 7) << 7;
+                wv_m = t2 & 0xffffu;
+                match_fields(head, (uint32_t)R.fm_idx, (uint32_t)R.fm_len, node_lenmin(R.fm_pl), R.fm_exp, sym, aux);
+                const uint32_t new_head = head + 1 == kRing ? 0 : head + 1;
+                const bool bump = node_lenmin(R.fm_pl) <= (uint32_t)R.fm_len && (uint32_t)R.fm_idx != new_head; // matcher.rs:66-71
+                const uint32_t lm = (uint32_t)R.fm_len + 1 < 127u ? (uint32_t)R.fm_len + 1 : 127u;
+                bump_pl = node_pos(R.fm_pl) | lm << 25;
+                fmw = (uint32_t)R.fm_len | (uint32_t)R.fm_idx << 8 | (bump ? 1u << 20 : 0u);
+            }
+            __threadfence_block();
+            if (bcast0(v_bver[c]) != v0) continue; // the bucket changed while it was being read: rebuild
+            // ---- publish ----
+            {
+                // ring-slot image as 32 int16: [0,1] pl = q, [2] expected (patched by the executor), [3] next[0] = h0,
+                // [4..31] next[1..28] = the old head's next[0..27]; lane L>=1 holds the old head's next[L-1] in f_next
+                const int up = __shfl_sync(kFull, f_next, lane >= 3 ? lane - 3 : 1);
+                int hv;
+                if (lane == 0) hv = (int)(q & 0xffffu);
+                else if (lane == 1) hv = (int)((q & 0x1ffffffu) >> 16);
+                else if (lane == 2) hv = 0;
+                else if (lane == 3) hv = h0;
+                else hv = up;
+                reinterpret_cast<int16_t *>(pub.rec)[lane] = (int16_t)hv;
+                pub.cand[lane] = (uint16_t)(cand_slot < 0 ? 0xffff : cand_slot);
+            }
+            if (lane == 0) {
+                const uint32_t m1 = R.max_d1 < 0 ? 0u : (R.max_d1 > 255 ? 255u : (uint32_t)R.max_d1);
+                const uint32_t m2 = R.max_d2 < 0 ? 0u : (R.max_d2 > 255 ? 255u : (uint32_t)R.max_d2);
+                pub.ver = v0;
+                pub.cmx = c | m1 << 8 | m2 << 16 | (single_round ? 1u << 24 : 0u);
+                pub.hc = h2 | (cur4 & 0xffffu) << 16;
+                pub.fm = fmw;
+                pub.sym = sym;
+                pub.aux = aux;
+                pub.bump_pl = bump_pl;
+                pub.e0 = e0;
+                pub.w_lit = hw_lit | wv_lit << 16;
+                pub.w_m = hw_m | wv_m << 16;
+                pub.fm_plexp = node_lenmin(R.fm_pl) << 8 | (R.fm_exp & 0xffu);
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) vpub->q = q;
+            my_q = q;
+            my_c = c;
+            my_ver = v0;
         }
-        after_literal = (it.symbol < 256) ? 1u : 0u;
-        spos = new_spos;
-        n_items++;
-        __threadfence_block();
-        __syncthreads();
+        if (lane == 0) {
+            atomicAdd(&S->dbg[4], nbuild);
+            atomicAdd(&S->dbg[5], nabort + (nreval << 32));
+        }
     }
-
     __syncthreads();
-    for (int i = tid; i < kNumCtx; i += kParseThreads) S->ctx_count[i] = s_cnt[i];
-    for (int i = tid; i < kNumBuckets; i += kParseThreads) S->bhead[i] = s_bhead[i];
-    if (tid == 0) {
-        S->spos = spos;
-        S->after_literal = after_literal;
-        S->n_items = n_items;
-    }
+    for (int i = tid; i < 32768 / 8; i += NT) reinterpret_cast<uint4 *>(S->words)[i] = reinterpret_cast<const uint4 *>(sh.words)[i];
+    for (int i = tid; i < kNumCtx; i += NT) S->ctx_count[i] = sh.cnt[i];
+    for (int i = tid; i < kNumBuckets; i += NT) S->bhead[i] = sh.bhead[i];
 }
-
 
 // LZEncoder::forward (lz.rs:82-87) in two grid-stride phases.
 // Phase 1 — Bucket::forward (matcher.rs:82-87): rebase every position, saturating at 0.
@@ -1011,7 +1267,19 @@ __global__ void __launch_bounds__(256) orz_enc_forward_kernel(EncStream *streams
 
 size_t emit_smem_bytes() { return sizeof(EmitShared); }
 
-void launch_parse(EncStream *d_streams, int n, cudaStream_t st) { orz_parse_kernel<<<n, kParseThreads, 0, st>>>(d_streams); }
+void launch_parse(EncStream *d_streams, int n, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(orz_parse_kernel<22, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseShared));
+        cudaFuncSetAttribute(orz_parse_kernel<11, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseShared));
+        attr_set = true;
+    }
+    // few streams: 16 builders hide more latency per stream; many streams: 8 builders, more streams per SM
+    const char *force = getenv("ORZ_B200_PARSE_BUILDERS");
+    const int nb = force ? atoi(force) : (n <= 2 * 148 ? 16 : 8);
+    if (nb == 16) orz_parse_kernel<22, 16><<<n, 22 * 32, sizeof(ParseShared), st>>>(d_streams);
+    else orz_parse_kernel<11, 8><<<n, 11 * 32, sizeof(ParseShared), st>>>(d_streams);
+}
 void launch_emit(EncStream *d_streams, int n, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {

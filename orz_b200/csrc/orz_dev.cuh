@@ -104,6 +104,7 @@ struct EncStream {
     uint32_t items_cap;
     uint32_t depth0, depth1, depth2; // LZCfg (lz.rs:32-37)
     int32_t self_driven;  // 1: stream mode (kernel runs the lib.rs loop), 0: chunk mode (host drives)
+    uint32_t dbg_flags;   // debug switches (ORZ_B200_DBG): 1 no re-stamp, 2 publish spos after the stores
     // mutable
     uint32_t bhead[kNumBuckets];
     uint32_t ctx_count[kNumCtx];
@@ -112,6 +113,7 @@ struct EncStream {
     uint64_t in_pos, out_pos;
     int32_t status;       // 0 running, 1 done, <0 error code
     uint32_t n_chunks;
+    unsigned long long dbg[8]; // stage A counters: steps, executor spin iterations (own / lazy1 / lazy2 probe), builds, aborted builds
 };
 
 // Per-stream decoder control block (lz.rs:348-357 LZDecoder, lib.rs:99-127 loop state)
