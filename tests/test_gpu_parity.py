@@ -40,3 +40,24 @@ def test_decode_matches_oracle(gen, n):
     data = getattr(datagen, gen)(n)
     comp = pyoracle.encode(data, 1)
     assert orz_b200.decode(comp, out_cap=n + 64) == data
+
+
+def test_gpu_matches_committed_golden_vectors():
+    """The committed oracle vectors (tests/golden/golden.json): the GPU must reproduce every hash."""
+    import hashlib
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+    cases = {"empty": b"", "a": b"a", "abcabc": b"abcabcabcabcabcabcabcabc", "fox": b"the quick brown fox jumps over the lazy dog. " * 20,
+             "text_64k": datagen.text_like(65536, seed=101), "random_20k": datagen.random_bytes(20000, seed=102),
+             "lowent_100k": datagen.low_entropy(100000, seed=103)}
+    for level in (0, 1, 2):
+        outs = orz_b200.encode_batch(list(cases.values()), level)
+        for (name, _), enc in zip(cases.items(), outs):
+            want = g["cases"][name]["levels"][str(level)]
+            assert (len(enc), hashlib.sha256(enc).hexdigest()) == (want["len"], want["sha256"]), (name, level)
+    e8 = datagen.enwik8(2_000_000)
+    if e8 is not None:
+        enc = orz_b200.encode(e8, 2)
+        want = g["enwik8_2M"]["levels"]["2"]
+        assert (len(enc), hashlib.sha256(enc).hexdigest()) == (want["len"], want["sha256"])
