@@ -223,23 +223,10 @@ def main():
         """North-star's final collective: all-gather of the per-stream compressed spans (lengths, then padded spans)."""
         if world <= 1:
             return
-        total = sum(batch.result_len(i) for i in range(n))
-        lens = torch.tensor([total], dtype=torch.int64, device=f"cuda:{dev}")
-        all_lens = [torch.zeros_like(lens) for _ in range(world)]
-        dist.all_gather(all_lens, lens)
-        mx = int(max(int(x.item()) for x in all_lens))
-        span = torch.zeros(mx, dtype=torch.uint8, device=f"cuda:{dev}")
-        off = 0
-        for i in range(n):
-            ln = batch.result_len(i)
-
-            class _W:
-                __cuda_array_interface__ = {"shape": (ln,), "typestr": "|u1", "data": (batch.result_dev(i), False), "version": 2}
-            if ln:
-                span[off:off + ln] = torch.as_tensor(_W(), device=f"cuda:{dev}")
-            off += ln
-        outb = [torch.empty_like(span) for _ in range(world)]
-        dist.all_gather(outb, span)
+        from orz_b200 import dist as odist
+        device = torch.device("cuda", dev)
+        spans = [odist.device_span(batch.result_dev(i), batch.result_len(i), device) for i in range(n)]
+        odist.gather_spans(spans, device)
         torch.cuda.synchronize()
 
     dev_ms, parse_ms, emit_ms, parse_launches, launches = [], [], [], [], []
