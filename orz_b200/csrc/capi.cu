@@ -414,7 +414,7 @@ extern "C" int orz_batch_run(orz_batch *b) {
             unsigned long long d[8] = {0};
             for (int i = 0; i < b->n; i++)
                 for (int k = 0; k < 8; k++) d[k] += tmp[i].dbg[k];
-            fprintf(stderr, "orz_b200 stage A: steps %llu, executor spins own %llu lazy1 %llu lazy2 %llu, builds %llu, aborted %llu, revalidated %llu; own-probe not ready at first poll: building %llu, other-q %llu, stale-version %llu\n", d[0], d[1],
+            fprintf(stderr, "orz_b200 stage A: steps %llu, executor spins own %llu lazy1 %llu lazy2 %llu, builds %llu, aborted %llu, seqlock-failed %llu; own-probe not ready at first poll: building %llu, other-q %llu, stale-version %llu\n", d[0], d[1],
                     d[2], d[3], d[4], d[5] & 0xffffffffull, d[5] >> 32, d[6] >> 32, d[6] & 0xffffffffull, d[7]);
         }
     } else {

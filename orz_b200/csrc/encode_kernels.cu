@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                     restamp_probe(&sh.pub[(new_spos + 1) % NS], new_spos + 1, c, ver, e0, new_head, bump_idx);
                     restamp_probe(&sh.pub[(new_spos + 2) % NS], new_spos + 2, c, ver, e0, new_head, bump_idx);
                 }
-                __threadfence_block();
+                if (!(dbg_flags & 16u)) __threadfence_block();
                 v_bver[c] = ver + 2;
                 sh.cnt[ctx] = seq + 1;
                 items[n_items] = it;
@@ -523,9 +523,11 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                 w1 = (unsigned long long)cyc_lazy;
                 w2 = (unsigned long long)(clock64() - t_start);
             }
-            S->dbg[1] += w0;
-            S->dbg[2] += w1;
-            S->dbg[3] += w2;
+            if (!(dbg_flags & 32u)) {
+                S->dbg[1] += w0;
+                S->dbg[2] += w1;
+                S->dbg[3] += w2;
+            }
             if (!wd_code) {
                 S->dbg[6] += ((unsigned long long)cz_building << 32) | cz_other;
                 S->dbg[7] += cz_stale;
@@ -537,6 +539,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
         // this builder's two published probes (positions b mod NB, NB apart): [0] lives in slot q % NS < NB ... by position
         uint32_t pq[2] = {kNone, kNone}, pc[2] = {0, 0}, pver[2] = {0, 0};
         unsigned long long nbuild = 0, nabort = 0, nreval = 0;
+        unsigned long long bcyc = 0, nvfail = 0, lead[4] = {0, 0, 0, 0};
         for (;;) {
             // Control values are read by every lane but only lane 0's copy is used (bcast0): lanes that are not
             // perfectly converged could otherwise see different values and part ways before a full-mask shuffle.
@@ -576,6 +579,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
             // ---- build the probe of q ----
             my_q = kNone;
             nbuild++;
+            const long long tb0 = clock64();
             if (lane == 0) vpub->q = kNone;
             __threadfence_block();
             const uint32_t prev4 = ld_u32_unaligned(win, q - 4); // bytes q-4 .. q-1
@@ -615,7 +619,10 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                 fmw = (uint32_t)R.fm_len | (uint32_t)R.fm_idx << 8 | (bump ? 1u << 20 : 0u);
             }
             __threadfence_block();
-            if (bcast0(v_bver[c]) != v0) continue; // the bucket changed while it was being read: rebuild
+            if (bcast0(v_bver[c]) != v0) { // the bucket changed while it was being read: rebuild
+                nvfail++;
+                continue;
+            }
             // ---- publish ----
             {
                 // ring-slot image as 32 int16: [0,1] pl = q, [2] expected (patched by the executor), [3] next[0] = h0,
@@ -651,10 +658,20 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
             my_q = q;
             my_c = c;
             my_ver = v0;
+            bcyc += clock64() - tb0;
+            {
+                const uint32_t d = q - bcast0(*v_spos);
+                lead[d >= 0x80000000u ? 0 : (d < 3 ? 0 : (d < 8 ? 1 : (d < 16 ? 2 : 3)))]++;
+            }
         }
         if (lane == 0) {
             atomicAdd(&S->dbg[4], nbuild);
-            atomicAdd(&S->dbg[5], nabort + (nreval << 32));
+            atomicAdd(&S->dbg[5], nabort + (nvfail << 32));
+            if (dbg_flags & 32u) { // builder timing report replaces the executor's spin counters
+                atomicAdd(&S->dbg[1], bcyc);
+                atomicAdd(&S->dbg[2], lead[0] | lead[1] << 32);
+                atomicAdd(&S->dbg[3], lead[2] | lead[3] << 32);
+            }
         }
     }
     __syncthreads();
