@@ -429,6 +429,11 @@ extern "C" int orz_batch_run(orz_batch *b) {
             b->result_len[i] = tmp[i].out_len;
             b->status[i] = tmp[i].status;
         }
+        if (getenv("ORZ_B200_STATS")) {
+            unsigned long long it = 0, ms = 0;
+            for (int i = 0; i < b->n; i++) it += tmp[i].dbg[0], ms += tmp[i].dbg[1];
+            fprintf(stderr, "orz_b200 decode: items %llu, rank-table cache misses %llu\n", it, ms);
+        }
     }
     b->timer.end(whole, b->st);
     CU_TRY(cudaStreamSynchronize(b->st));

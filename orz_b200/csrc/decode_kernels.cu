@@ -6,6 +6,8 @@
 // tables and rebase the ring at block boundaries.  Throughput comes from many streams in flight.
 #include "orz_dev.cuh"
 
+#include <cstdlib>
+
 namespace orz {
 
 constexpr int kLutBits = 11;
@@ -27,7 +29,33 @@ struct DecShared {
     uint16_t bhead[kNumBuckets];
     uint16_t vs[kSymStride + 8];
     uint32_t num_counted;
+    int16_t ctag[128];   // rank-table cache tags (context id, -1 = empty)
 };
+
+// Direct-mapped, write-back cache of rank tables in shared memory (few-stream launches: one block per SM).
+// Every item reads and writes its context's table; in global memory each store evicts the line from L1, so the
+// four dependent loads of symrank.rs:49-97 each cost an L2 round trip.  Called by the whole warp in lock step.
+template <int CACHE>
+__device__ __forceinline__ SymRank *rank_table(SymRank *symranks, SymRank *cache, int16_t *ctag, uint32_t ctx, unsigned &misses) {
+    if (CACHE == 0) return &symranks[ctx];
+    const uint32_t slot = ((ctx & 0x7fu) + 43u * (ctx >> 7)) & (uint32_t)(CACHE - 1);
+    const int tag = ctag[slot];
+    if (tag != (int)ctx) { // warp-cooperative swap: 394 words out, 394 words in
+        misses++;
+        const int lane = threadIdx.x & 31;
+        uint32_t *c32 = reinterpret_cast<uint32_t *>(&cache[slot]);
+        if (tag >= 0) {
+            uint32_t *g32 = reinterpret_cast<uint32_t *>(&symranks[tag]);
+            for (int i = lane; i < (int)(sizeof(SymRank) / 4); i += 32) g32[i] = c32[i];
+        }
+        __syncwarp();
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(&symranks[ctx]);
+        for (int i = lane; i < (int)(sizeof(SymRank) / 4); i += 32) c32[i] = s32[i];
+        ctag[slot] = (int16_t)ctx;
+        __syncwarp();
+    }
+    return &cache[slot];
+}
 
 struct BitReader { // coder.rs:91-157,159-196
     const uint8_t *base; // 4 B aligned
@@ -139,8 +167,7 @@ __device__ __forceinline__ int decode_sym(BitReader &br, const HuffDec &h) { // 
 }
 
 // symrank.rs:61-97 on a table in global memory
-__device__ __forceinline__ void symrank_update(SymRank *s, uint32_t v, uint32_t i) {
-    uint32_t ecnt = s->cnt, esum = s->sum;
+__device__ __forceinline__ void symrank_update(SymRank *s, uint32_t v, uint32_t i, uint32_t ecnt, uint32_t esum) {
     if (ecnt > (uint32_t)kNumSym) {
         ecnt = ecnt * 9 / 10;
         esum = esum * 9 / 10;
@@ -172,14 +199,17 @@ __device__ __forceinline__ void symrank_update(SymRank *s, uint32_t v, uint32_t 
     }
 }
 
+template <int CACHE>
 __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
     DecStream *S = &streams[blockIdx.x];
     if (S->status != 0) return;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
+    SymRank *cache = reinterpret_cast<SymRank *>(smem_raw + ((sizeof(DecShared) + 15) & ~size_t(15)));
     const int lane = threadIdx.x;
 
     for (int i = lane; i < kNumBuckets; i += 32) sh.bhead[i] = (uint16_t)S->bhead[i];
+    for (int i = lane; i < 128; i += 32) sh.ctag[i] = -1;
     Node *nodes = S->nodes;
     uint16_t *words = S->words;
     SymRank *symranks = S->symranks;
@@ -193,6 +223,8 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
     uint32_t after_literal = S->after_literal;
     uint32_t first_block = S->first_block;
     uint32_t n_chunks = 0;
+    unsigned misses = 0;
+    unsigned long long items_done = 0;
     int status = 0;
     __syncwarp();
 
@@ -241,7 +273,7 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
         br.bb = 0;
         br.bl = 0;
         uint32_t sbuf_len = 0, n_items = 0;
-        if (lane == 0) {
+        { // every lane parses the header (same loads, same values): no broadcast needed, all lanes stay usable
             if (first_block) {
                 uint32_t num = br.varint();
                 if (num > (uint32_t)kNumSym) status = -1;
@@ -301,7 +333,8 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
 
         // ---- items (lz.rs:411-476): the serial chain, lane 0 ----
         const uint32_t spos_start = spos;
-        if (lane == 0) {
+        { // the serial chain, executed by every lane in lock step: identical loads, identical (redundant) stores, so
+          // each lane sees its own writes and all 32 lanes are at hand for the cooperative copies
             // window position p lives at win[p]; `wa`/`dl` give a 16 B aligned base for dword accesses
             // (stream mode decodes in place: position PREMATCH of the current block is out[blk_apos]).
             uint8_t *wa = self_driven ? (S->out + blk_apos - kBlockNew) : S->win;
@@ -317,7 +350,8 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
                 const uint32_t c = (b_m1 & 0x7fu) | is_alnum(b_m2) << 7;
                 const uint32_t h2 = (b_m1 & 0x7fu) | ((b_m2 & 0x7fu) | is_alnum(b_m3) << 7) << 7;
                 const uint32_t lwe = words[h2];
-                SymRank *sr = &symranks[c | after_literal << 8];
+                SymRank *sr = rank_table<CACHE>(symranks, cache, sh.ctag, c | after_literal << 8, misses);
+                const uint32_t ecnt0 = sr->cnt, esum0 = sr->sum; // issued early: independent of the bit stream
                 const uint32_t iun = sr->index[lwe & 0xffu];
                 const int sym = decode_sym(br, sh.h[after_literal]);
                 if (sym < 0) {
@@ -330,7 +364,7 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
                     break;
                 }
                 const uint32_t v = sr->value[i];
-                symrank_update(sr, v, i);
+                symrank_update(sr, v, i, ecnt0, esum0);
 
                 Node *bn = nodes + c * kNodesStride;
                 const uint32_t head = sh.bhead[c];
@@ -377,8 +411,9 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
                         break;
                     }
                     const uint32_t node = (head + kRing - ro) % kRing;
-                    const uint32_t pl = bn[node].pl;
-                    uint32_t mexp = bn[node].expected;
+                    const unsigned long long nrec = *reinterpret_cast<const unsigned long long *>(&bn[node]);
+                    const uint32_t pl = (uint32_t)nrec;
+                    uint32_t mexp = (uint32_t)(nrec >> 48) & 0xffu;
                     uint32_t eml = lenid;
                     if (lenid == (uint32_t)(kLenidSize - 1)) {
                         const int e2 = decode_sym(br, sh.h[2]);
@@ -413,25 +448,41 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
                     bn[new_head] = nn;
                     sh.bhead[c] = (uint16_t)new_head;
                     after_literal = 0;
-                    // mem.rs:74-92: semantically a byte-serial overlapped copy
+                    // mem.rs:74-92: semantically a byte-serial overlapped copy.  The tail bytes needed for the next
+                    // hashes are carried in registers: a load right after a store to the same line misses L1.
                     const uint32_t dist = spos - mpos;
+                    uint32_t y5;
                     if (dist >= 4) {
+                        uint32_t lo = prev4, hi = 0, left = 0;
                         for (uint32_t q = 0; q < mlen; q += 4) {
                             const uint32_t wv = ld_u32_unaligned(wa, mpos + q + dl);
-                            const uint32_t left = mlen - q;
+                            left = mlen - q;
                             win[spos + q] = (uint8_t)wv;
                             if (left > 1) win[spos + q + 1] = (uint8_t)(wv >> 8);
                             if (left > 2) win[spos + q + 2] = (uint8_t)(wv >> 16);
                             if (left > 3) win[spos + q + 3] = (uint8_t)(wv >> 24);
+                            if (q) lo = hi;
+                            hi = wv;
                         }
-                    } else {
-                        for (uint32_t q = 0; q < mlen; q++) win[spos + q] = win[mpos + q];
+                        if (left > 4) left = 4; // the last iteration wrote `left` bytes of hi after the 4 bytes of lo
+                        const unsigned long long both = (unsigned long long)hi << 32 | lo;
+                        y5 = (uint32_t)(both >> (8 * (left - 1))) & 0xffu; // byte end-5
+                        prev4 = (uint32_t)(both >> (8 * left));            // bytes end-4 .. end-1
+                    } else { // period-dist run: replicate the last `dist` bytes from registers
+                        uint32_t pat = prev4 >> (8 * (4 - dist)); // the last dist bytes, lowest address first
+                        y5 = 0;
+                        for (uint32_t q = 0; q < mlen; q++) {
+                            const uint32_t byte = pat & 0xffu;
+                            win[spos + q] = (uint8_t)byte;
+                            y5 = prev4 & 0xffu;
+                            prev4 = (prev4 >> 8) | byte << 24;
+                            pat = (pat >> 8) | byte << (8 * (dist - 1)); // rotate within dist bytes
+                        }
+                        // y5 must be byte end-5: prev4 before the last shift held end-5 in its lowest byte
                     }
                     spos += mlen;
-                    const uint32_t t4 = ld_u32_unaligned(wa, spos - 5 + dl); // bytes spos-5 .. spos-2
-                    prev4 = ld_u32_unaligned(wa, spos - 4 + dl);
-                    const uint32_t y3 = (t4 >> 16) & 0xffu, y4 = (t4 >> 8) & 0xffu, y5 = t4 & 0xffu;
-                    const uint32_t hw = (y3 & 0x7fu) | ((y4 & 0x7fu) | is_alnum(y5) << 7) << 7;
+                    const uint32_t y4 = prev4 & 0xffu, y3 = (prev4 >> 8) & 0xffu;
+                    const uint32_t hw = (y3 & 0x7fu) | ((y4 & 0x7fu) | is_alnum(y5) << 7) << 7; // hash2(spos-3)
                     words[hw] = (uint16_t)(prev4 >> 16);
                 }
             }
@@ -445,6 +496,7 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
         const uint32_t spos_end = __shfl_sync(0xffffffffu, spos, 0);
         after_literal = __shfl_sync(0xffffffffu, after_literal, 0);
         n_chunks++;
+        items_done += n_items;
         if (status != 0) break;
         __threadfence_block();
         __syncwarp();
@@ -474,6 +526,16 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
     }
 
     __syncwarp();
+    if (CACHE > 0) { // write the cached rank tables back (the state persists across chunk-mode calls)
+        for (int sl = 0; sl < CACHE; sl++) {
+            const int tag = sh.ctag[sl];
+            if (tag < 0) continue;
+            const uint32_t *c32 = reinterpret_cast<const uint32_t *>(&cache[sl]);
+            uint32_t *g32 = reinterpret_cast<uint32_t *>(&symranks[tag]);
+            for (int i = lane; i < (int)(sizeof(SymRank) / 4); i += 32) g32[i] = c32[i];
+        }
+    }
+    __syncwarp();
     for (int i = lane; i < kNumBuckets; i += 32) S->bhead[i] = sh.bhead[i];
     if (lane == 0) {
         S->spos = spos;
@@ -482,6 +544,8 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
         S->out_len = out_len;
         S->in_pos = in_pos;
         S->n_chunks += n_chunks;
+        S->dbg[0] += items_done;
+        S->dbg[1] += misses;
         S->status = self_driven ? status : (status == 0 ? 0 : status);
     }
 }
@@ -500,12 +564,20 @@ __global__ void __launch_bounds__(256) orz_dec_forward_kernel(DecStream *streams
 }
 
 void launch_decode(DecStream *d_streams, int n, cudaStream_t st) {
+    constexpr size_t base = (sizeof(DecShared) + 15) & ~size_t(15);
+    constexpr size_t big = base + 128 * sizeof(SymRank);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(orz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
+        cudaFuncSetAttribute(orz_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big);
+        cudaFuncSetAttribute(orz_decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
         attr_set = true;
     }
-    orz_decode_kernel<<<n, 32, sizeof(DecShared), st>>>(d_streams);
+    // few streams: one block per SM with 128 rank tables cached in shared memory; many streams: several blocks per SM
+    const char *force = getenv("ORZ_B200_DEC_CACHE");
+    // measured in round 1: the cache does not pay (misses ~17 % of items, a swap costs as much as it saves): off by default
+    const bool cached = force ? atoi(force) != 0 : false;
+    if (cached) orz_decode_kernel<128><<<n, 32, big, st>>>(d_streams);
+    else orz_decode_kernel<0><<<n, 32, base, st>>>(d_streams);
 }
 void launch_dec_forward(DecStream *d_stream, uint32_t forward_len, cudaStream_t st) {
     orz_dec_forward_kernel<<<148, 256, 0, st>>>(d_stream, forward_len);

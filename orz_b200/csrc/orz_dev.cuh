@@ -134,6 +134,7 @@ struct DecStream {
     uint64_t in_pos;
     int32_t status;
     uint32_t n_chunks;
+    unsigned long long dbg[4]; // items, rank-table cache misses
 };
 
 // ---- small device helpers --------------------------------------------------------------------

@@ -12,10 +12,11 @@ def main():
     nstreams = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     level = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     check = (sys.argv[4] != "nocheck") if len(sys.argv) > 4 else True
-    full = datagen.enwik8(n * nstreams)
+    full = datagen.enwik8(min(n * nstreams, 100_000_000))
     if full is None:
-        full = datagen.text_like(n * nstreams)
-    segs = [full[i * n:(i + 1) * n] for i in range(nstreams)]
+        full = datagen.text_like(min(n * nstreams, 50_000_000))
+    nseg = max(1, len(full) // n)
+    segs = [full[(i % nseg) * n:((i % nseg) + 1) * n] for i in range(nstreams)]  # tiles the corpus when it is too short
     b = Batch(Batch.ENCODE, [len(s) for s in segs], cfg=level)
     for i, s in enumerate(segs):
         b.upload(i, s)
