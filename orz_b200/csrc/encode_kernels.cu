@@ -283,7 +283,7 @@ struct ParseShared {
     uint4 chg[kNumBuckets];        // last insertion per bucket: {version after it, hash entry, slot written, bumped slot + 1}
     uint32_t spos;                 // published parse position
     uint32_t done;
-    ProbePub pub[4 * kMaxBuilders]; // slot of position q: q % (LM * NB); builder b owns the positions q % NB == b
+    ProbePub pub[2 * kMaxBuilders]; // slot of position q: q % (2 * NB); builder b owns the positions q % NB == b
 };
 
 // The executor (one thread) just inserted (slot new_head, hash entry e0, optional lenmin bump of slot bump_idx)
@@ -328,9 +328,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
     ParseShared &sh = *reinterpret_cast<ParseShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NT = NW * 32;
-    // probe slots = lookahead in positions: LM slots per builder (2 by default; ORZ_B200_DBG bits 8-9 override: 0 -> 2, 1 -> 3, 2 -> 4)
-    const int LM = 2 + (int)((S->dbg_flags >> 8) & 3u) > 4 ? 4 : 2 + (int)((S->dbg_flags >> 8) & 3u);
-    const uint32_t NS = (uint32_t)(LM * NB);
+    constexpr int NS = 2 * NB; // probe slots = lookahead in positions
 
     for (int i = tid; i < kNumCtx; i += NT) sh.cnt[i] = 0;
     for (int i = tid; i < kNumBuckets; i += NT) {
@@ -338,7 +336,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
         sh.bver[i] = 0;
     }
     for (int i = tid; i < 32768 / 8; i += NT) reinterpret_cast<uint4 *>(sh.words)[i] = reinterpret_cast<const uint4 *>(S->words)[i];
-    for (int i = tid; i < 4 * NB; i += NT) sh.pub[i].q = kNone;
+    if (tid < 2 * NB) sh.pub[tid].q = kNone;
     const uint8_t *win = S->win;
     ENode *nodes = S->nodes;
     int16_t *heads = S->heads;
@@ -539,7 +537,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
         // ------------------------------------------------------------------ builders
         const int b = warp - 1 - (warp >> 2);
         // this builder's two published probes (positions b mod NB, NB apart): [0] lives in slot q % NS < NB ... by position
-        uint32_t pq[4] = {kNone, kNone, kNone, kNone}, pc[4] = {0, 0, 0, 0}, pver[4] = {0, 0, 0, 0};
+        uint32_t pq[2] = {kNone, kNone}, pc[2] = {0, 0}, pver[2] = {0, 0};
         unsigned long long nbuild = 0, nabort = 0, nreval = 0;
         unsigned long long bcyc = 0, nvfail = 0, lead[4] = {0, 0, 0, 0};
         for (;;) {
@@ -551,9 +549,10 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
             // pick the nearer of its two positions that has no current probe
             uint32_t q = kNone;
             int k = 0;
-            for (int t = 0; t < LM; t++) {
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
                 const uint32_t qt = q1 + t * NB;
-                const int kt = (int)((qt / NB) % (uint32_t)LM);
+                const int kt = (int)((qt / NB) & 1u);
                 bool ok = qt >= sbuf_len;
                 if (!ok && pq[kt] == qt) {
                     const uint32_t bv = bcast0(v_bver[pc[kt]]);
