@@ -117,6 +117,8 @@ def main():
     ap.add_argument("--workload", default="exact", choices=["exact", "segments"])
     ap.add_argument("--segment-bytes", type=int, default=1 << 20)
     ap.add_argument("--bytes", type=int, default=N_BYTES, help="debug only: shrink the corpus (prints invalid:true)")
+    ap.add_argument("--direction", default="encode", choices=["encode", "decode"],
+                    help="decode: BASELINE configs[4], the oracle-compressed corpus decoded on the GPU (extra line, not the headline metric)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -131,13 +133,19 @@ def main():
     else:
         sb = args.segment_bytes
         streams = [data[i:i + sb] for i in range(0, data.size, sb)]
-        wl = (f"segment-parallel (extension): {args.bytes:,} B corpus as {len(streams)} independent orz streams of "
-              f"{sb:,} B per GPU, -l{LEVEL}")
+        n_all = len(streams)
+        if world > 1:  # independent streams shard across ranks (stream i -> rank i % N); total work is fixed
+            from orz_b200.dist import shard_streams
+            streams = [streams[i] for i in shard_streams(n_all, rank, world)]
+        wl = (f"segment-parallel (extension): {args.bytes:,} B corpus as {n_all} independent orz streams of {sb:,} B "
+              f"sharded over {world} GPU(s), -l{LEVEL}")
     config = {"workload": wl, "level": LEVEL, "mode": "exact-stream" if args.workload == "exact" else "segment-parallel",
               "streams_per_gpu": len(streams), "multi_gpu": "replicas only (one orz stream does not shard)",
               "l2": "L2 flushed between timed iterations (256 MiB write)"}
-    base = {"metric": METRIC, "unit": "MB/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+    sharded = args.workload == "segments" and world > 1
+    base = {"metric": METRIC if args.direction == "encode" else "decode MB/s on the oracle-compressed corpus (BASELINE configs[4])",
+            "unit": "MB/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8",
             "data": ("real: " if "enwik8 (" in data_desc or "tiled" in data_desc else "synthetic: ") + data_desc,
             "config": config}
     if args.bytes != N_BYTES:
@@ -157,11 +165,20 @@ def main():
             work = streams * 1
         nthreads = min(len(work), cores)
         times = []
+        from concurrent.futures import ThreadPoolExecutor
+        if args.direction == "decode":  # reference-compressed inputs, timed: the oracle's decoder on all usable host threads
+            sizes = [int(np.asarray(w).size) for w in work]
+            with ThreadPoolExecutor(nthreads) as ex:
+                comp = list(ex.map(lambda s: pyoracle.encode(s, LEVEL), work))
         for it in range(args.warmup + args.steps):
-            if args.workload == "exact":
+            if args.direction == "decode":
+                t0 = time.perf_counter()
+                with ThreadPoolExecutor(nthreads) as ex:
+                    list(ex.map(lambda cs: pyoracle.decode(cs[0], cs[1] + 64), zip(comp, sizes)))
+                dt = time.perf_counter() - t0
+            elif args.workload == "exact":
                 dt, _ = oracle_encode_threads(work, LEVEL)
             else:  # independent segments over all cores
-                from concurrent.futures import ThreadPoolExecutor
                 t0 = time.perf_counter()
                 with ThreadPoolExecutor(nthreads) as ex:
                     list(ex.map(lambda s: pyoracle.encode(s, LEVEL), work))
@@ -200,8 +217,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    decode_dir = args.direction == "decode"
+    if decode_dir:  # the inputs of the hot path are the oracle-compressed streams (reference-compressed, BASELINE configs[4])
+        from oracle import pyoracle
+        raw_streams = streams
+        streams = [np.frombuffer(pyoracle.encode(s, LEVEL), dtype=np.uint8) for s in raw_streams]
+        raw_lens = [int(s.size) for s in raw_streams]
     in_lens = [int(s.size) for s in streams]
-    batch = Batch(Batch.ENCODE, in_lens, cfg=LEVEL, device=dev)
+    if decode_dir:
+        batch = Batch(Batch.DECODE, in_lens, out_caps=[r + 64 for r in raw_lens], device=dev)
+    else:
+        batch = Batch(Batch.ENCODE, in_lens, cfg=LEVEL, device=dev)
     for i, s in enumerate(streams):
         batch.upload(i, s)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")
@@ -210,7 +236,7 @@ def main():
     L = load()
     cfg = LZCfg.from_level(LEVEL)
     pin_in = [torch.from_numpy(np.ascontiguousarray(s)).pin_memory() for s in streams]
-    caps = [L.orz_encode_bound(n) for n in in_lens]
+    caps = [r + 64 for r in raw_lens] if decode_dir else [L.orz_encode_bound(n) for n in in_lens]
     pin_out = [torch.empty(c, dtype=torch.uint8).pin_memory() for c in caps]
     n = len(streams)
     inp = (C.c_void_p * n)(*[t.data_ptr() for t in pin_in])
@@ -246,9 +272,9 @@ def main():
         if it >= args.warmup:
             wall.append(t1 - t0)
             dev_ms.append(batch.timing(4)[0])
-            pm, pk = batch.timing(0)
-            em, ek = batch.timing(1)
-            bm, bk = batch.timing(2)
+            pm, pk = batch.timing(3 if decode_dir else 0)
+            em, ek = (0.0, 0) if decode_dir else batch.timing(1)
+            bm, bk = (0.0, 0) if decode_dir else batch.timing(2)
             parse_ms.append(pm)
             emit_ms.append(em)
             parse_launches.append(pk)
@@ -259,7 +285,10 @@ def main():
         flush.fill_((it + 1) & 0xFF)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        check(L.orz_encode_batch(dev, C.byref(cfg), n, inp, inl, outp, outc, outl), "orz_encode_batch")
+        if decode_dir:
+            check(L.orz_decode_batch(dev, n, inp, inl, outp, outc, outl), "orz_decode_batch")
+        else:
+            check(L.orz_encode_batch(dev, C.byref(cfg), n, inp, inl, outp, outc, outl), "orz_encode_batch")
         t1 = time.perf_counter()
         if it >= args.warmup:
             e2e_s.append(t1 - t0)
@@ -270,14 +299,19 @@ def main():
     # cross-check e2e output against the resident run
     assert sum(int(outl[i]) for i in range(n)) == comp_bytes
     total_in = sum(in_lens)
+    plain_bytes = sum(raw_lens) if decode_dir else total_in   # MB/s are uncompressed bytes per second, like progress.rs:72-83
 
     # max over ranks of the per-step device time (+ gather for N>1, measured by wall clock around a device sync)
     step_s = (sum(dev_ms) / len(dev_ms)) / 1e3 if world == 1 else sum(wall) / len(wall)
     e2e_step_s = sum(e2e_s) / len(e2e_s)
+    plain_all, in_all, out_all = plain_bytes, total_in, comp_bytes
     if world > 1:
         tt = torch.tensor([step_s, e2e_step_s], dtype=torch.float64, device=f"cuda:{dev}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         step_s, e2e_step_s = float(tt[0]), float(tt[1])
+        ts = torch.tensor([plain_bytes, total_in, comp_bytes], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        plain_all, in_all, out_all = (int(x) for x in ts.tolist())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -297,30 +331,35 @@ def main():
             traffic = None
     out = dict(base)
     out.update({
-        "value": n_gpus * total_in / step_s / 1e6,
+        "value": plain_all / step_s / 1e6,
         "ms_per_step": step_s * 1e3,
-        "e2e": {"value": n_gpus * total_in / e2e_step_s / 1e6, "unit": "MB/s", "h2d_bytes_per_step": total_in,
-                "d2h_bytes_per_step": comp_bytes},
+        "e2e": {"value": plain_all / e2e_step_s / 1e6, "unit": "MB/s", "h2d_bytes_per_step": in_all,
+                "d2h_bytes_per_step": out_all},
         "gpu_launches": int(sum(launches)),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "orz_parse_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "orz_decode_kernel" if decode_dir else "orz_parse_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes / p_launch, "launches_per_step": p_launch,
                      "avg_launch_ms": p_ms / p_launch,
                      "note": "latency-bound serial parse: one warp per stream; the fraction is expected to be ~1e-6..1e-4"},
-        "kernel_ms_per_step": {"parse": p_ms, "emit": sum(emit_ms) / len(emit_ms)},
-        "compressed_bytes": comp_bytes,
+        "kernel_ms_per_step": ({"decode": p_ms} if decode_dir else {"parse": p_ms, "emit": sum(emit_ms) / len(emit_ms)}),
+        "compressed_bytes": total_in if decode_dir else comp_bytes,
     })
     # CPU baseline: the oracle on this box's host cores, one stream = one core (the reference is single-threaded)
     if n_gpus == 1:
         from oracle import pyoracle
         pyoracle.build()
-        sample = streams[0] if args.workload == "exact" else data
+        sample = (raw_streams[0] if decode_dir else streams[0]) if args.workload == "exact" else data
         best = None
         want = None
         for _ in range(2):
-            t0 = time.perf_counter()
-            want = pyoracle.encode(sample, LEVEL)
+            if decode_dir:
+                comp0 = pyoracle.encode(sample, LEVEL) if args.workload != "exact" else streams[0]
+                t0 = time.perf_counter()
+                want = pyoracle.decode(comp0, int(np.asarray(sample).size) + 64)
+            else:
+                t0 = time.perf_counter()
+                want = pyoracle.encode(sample, LEVEL)
             dt = time.perf_counter() - t0
             best = dt if best is None or dt < best else best
         ours = batch.download(0) if args.workload == "exact" else None

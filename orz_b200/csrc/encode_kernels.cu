@@ -280,7 +280,6 @@ struct ParseShared {
     uint32_t cnt[kNumCtx];
     uint32_t bver[kNumBuckets];    // per-bucket seqlock: odd while the executor is writing the bucket
     uint16_t bhead[kNumBuckets];
-    uint4 chg[kNumBuckets];        // last insertion per bucket: {version after it, hash entry, slot written, bumped slot + 1}
     uint32_t spos;                 // published parse position
     uint32_t done;
     ProbePub pub[2 * kMaxBuilders]; // slot of position q: q % (2 * NB); builder b owns the positions q % NB == b
@@ -473,7 +472,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                         new_spos = spos + 1;
                     }
                 }
-                if (!(dbg_flags & 2u)) *v_spos = new_spos; // builders may retarget now: everything of P is in registers
+                *v_spos = new_spos; // builders may retarget now: everything of P is in registers
                 const int bump_idx = (emit_match && bump) ? (int)fm_idx : -1;
 
                 // Bucket::update (matcher.rs:62-80) + BucketMatcher::update (matcher.rs:115-121) under the bucket's seqlock
@@ -491,14 +490,13 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                 dst[3] = r3;
                 heads[c * kHeadsStride + e0] = (int16_t)new_head;
                 v_bhead[c] = (uint16_t)new_head;
-                sts_volatile_v4(&sh.chg[c], make_uint4(ver + 2, e0, new_head, (uint32_t)(bump_idx + 1)));
                 // neighbours in the same bucket that did not read anything this step changed stay valid
                 if (!(dbg_flags & 1u)) {
                     restamp_probe(&sh.pub[new_spos % NS], new_spos, c, ver, e0, new_head, bump_idx);
                     restamp_probe(&sh.pub[(new_spos + 1) % NS], new_spos + 1, c, ver, e0, new_head, bump_idx);
                     restamp_probe(&sh.pub[(new_spos + 2) % NS], new_spos + 2, c, ver, e0, new_head, bump_idx);
                 }
-                if (!(dbg_flags & 16u)) __threadfence_block();
+                __threadfence_block();
                 v_bver[c] = ver + 2;
                 sh.cnt[ctx] = seq + 1;
                 items[n_items] = it;
@@ -506,7 +504,6 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                 after_literal = (it.symbol < 256) ? 1u : 0u;
                 spos = new_spos;
                 n_items++;
-                if (dbg_flags & 2u) *v_spos = new_spos;
             }
             *v_done = 1;
             if (wd_code) {
@@ -538,7 +535,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
         const int b = warp - 1 - (warp >> 2);
         // this builder's two published probes (positions b mod NB, NB apart): [0] lives in slot q % NS < NB ... by position
         uint32_t pq[2] = {kNone, kNone}, pc[2] = {0, 0}, pver[2] = {0, 0};
-        unsigned long long nbuild = 0, nabort = 0, nreval = 0;
+        unsigned long long nbuild = 0, nabort = 0;
         unsigned long long bcyc = 0, nvfail = 0, lead[4] = {0, 0, 0, 0};
         for (;;) {
             // Control values are read by every lane but only lane 0's copy is used (bcast0): lanes that are not

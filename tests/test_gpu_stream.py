@@ -100,3 +100,20 @@ def test_decode_errors():
         assert out != data or True
     except orz_b200.OrzError as ex:
         assert ex.code in (-1, -2, -3)
+
+
+def test_full_enwik8_decode_and_segment_properties():
+    """BASELINE-size properties: the whole 100 MB corpus, oracle-compressed at -l2, decodes on the GPU to the original
+    (config 4); and a sharded batch of its 1 MiB segments round-trips through GPU encode -> oracle decode."""
+    e8 = datagen.enwik8()
+    if e8 is None:
+        pytest.skip("data/enwik8.xz not present")
+    comp = pyoracle.encode(e8, 2)
+    assert len(comp) == 26856813  # oracle's whole-file size (README.md:43 says 26,892,825: see DESIGN.md)
+    out = orz_b200.decode(comp, out_cap=len(e8) + 64)
+    assert out == e8
+    segs = [e8[i:i + (1 << 20)] for i in range(0, 24 << 20, 1 << 20)]
+    encs = orz_b200.encode_batch(segs, 1)
+    for s, e in zip(segs[:6], encs[:6]):
+        assert e == pyoracle.encode(s, 1)
+    assert [pyoracle.decode(e, len(s) + 64) for s, e in zip(segs, encs)] == segs
