@@ -478,19 +478,58 @@ extern "C" int orz_batch_timing(orz_batch *b, int cls, float *total_ms, int *lau
 // ------------------------------------------------------------------------------------------------
 // stream / batch entry points with host buffers (lib.rs:58-92, 94-129)
 // ------------------------------------------------------------------------------------------------
+// Host-buffer calls keep their last arena: allocating (and freeing) tens of MB of ring state per stream costs more
+// than the kernels for short inputs.  One cached batch per process, reused when the shape of the call repeats.
+#include <mutex>
+namespace {
+struct BatchCache {
+    std::mutex mu;
+    orz_batch *b = nullptr;
+    int device = -1, mode = -1, n = 0;
+    orz_lzcfg cfg{};
+    std::vector<size_t> in_cap, out_cap;
+    ~BatchCache() {
+        if (b) batch_destroy(b);
+    }
+} g_cache;
+} // namespace
+
 static int run_host_batch(int device, int mode, const orz_lzcfg *cfg, int n, const uint8_t *const *in, const size_t *in_len,
                           uint8_t *const *out, const size_t *out_cap, size_t *out_len) {
     if (n <= 0 || !in || !in_len || !out || !out_cap || !out_len) return ORZ_EARG;
-    int err;
-    std::vector<size_t> dev_cap(out_cap, out_cap + n);
-    orz_batch *b = batch_create(device, mode, cfg, n, in_len, dev_cap.data(), false, &err);
-    if (!b) return err;
+    std::lock_guard<std::mutex> lock(g_cache.mu);
+    bool reuse = g_cache.b && g_cache.device == device && g_cache.mode == mode && g_cache.n == n &&
+                 (mode != 0 || (cfg->match_depth == g_cache.cfg.match_depth && cfg->lazy_match_depth1 == g_cache.cfg.lazy_match_depth1 &&
+                                cfg->lazy_match_depth2 == g_cache.cfg.lazy_match_depth2));
+    for (int i = 0; reuse && i < n; i++)
+        // same window class (one-block or full) and enough room
+        reuse = in_len[i] <= g_cache.in_cap[i] && out_cap[i] <= g_cache.out_cap[i] &&
+                (mode != 0 || ((in_len[i] <= kBlockNew) == (g_cache.in_cap[i] <= kBlockNew) && in_len[i] * 2 >= g_cache.in_cap[i]));
+    if (!reuse) {
+        if (g_cache.b) batch_destroy(g_cache.b);
+        g_cache.b = nullptr;
+        int err;
+        std::vector<size_t> dev_cap(out_cap, out_cap + n);
+        orz_batch *nb = batch_create(device, mode, cfg, n, in_len, dev_cap.data(), false, &err);
+        if (!nb) return err;
+        g_cache.b = nb;
+        g_cache.device = device;
+        g_cache.mode = mode;
+        g_cache.n = n;
+        if (cfg) g_cache.cfg = *cfg;
+        g_cache.in_cap.assign(in_len, in_len + n);
+        g_cache.out_cap.assign(out_cap, out_cap + n);
+    }
+    orz_batch *b = g_cache.b;
     int rc = ORZ_OK;
     for (int i = 0; i < n && rc == ORZ_OK; i++) rc = orz_batch_upload(b, i, in[i], in_len[i]);
     if (rc == ORZ_OK) rc = orz_batch_run(b);
     if (rc == ORZ_OK)
         for (int i = 0; i < n && rc == ORZ_OK; i++) rc = orz_batch_download(b, i, out[i], out_cap[i], &out_len[i]);
-    batch_destroy(b);
+    if (rc != ORZ_OK) { // do not keep an arena in an unknown state
+        batch_destroy(b);
+        g_cache.b = nullptr;
+    }
     return rc;
 }
 
