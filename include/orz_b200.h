@@ -113,6 +113,21 @@ int orz_batch_download(orz_batch *, int stream, uint8_t *host, size_t cap, size_
 /* device pointer of stream i's result (for NCCL gathers of compressed spans) */
 void *orz_batch_result_dev(orz_batch *, int stream);
 
+/* =====================================================================================
+ * Segment container (extension; the reference format has no index, size or checksum).
+ *   "ORZS" u8 version=1 u8 level u16 0 | u64 raw_len | u32 segment_size | u32 n_segments |
+ *   n_segments x { u32 raw_len, u32 comp_len, u32 crc32(raw) } | the n_segments orz streams back to back
+ * Every segment is an independent orz stream, byte-identical to `orz encode` of that segment alone, so segments encode
+ * and decode concurrently (one thread block each) and shard across GPUs.  A reference `orz decode` fed one stream
+ * extracted from the container decodes that segment.  All integers little endian.
+ * ===================================================================================== */
+size_t orz_segmented_bound(size_t n, size_t segment_size);
+int orz_encode_segmented(int device, const orz_lzcfg *cfg, int level_tag, const uint8_t *in, size_t n, size_t segment_size,
+                         uint8_t *out, size_t out_cap, size_t *out_len);
+/* raw size recorded in a container header (ORZ_EINVAL if `in` is not a container) */
+int orz_segmented_raw_len(const uint8_t *in, size_t n, size_t *raw_len);
+int orz_decode_segmented(int device, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *out_len);
+
 /* Kernel timing of the last run(): CUDA-event milliseconds and launch counts per kernel class
  * (0 parse/stage A, 1 emit/stages B-D, 2 block load/slide/forward, 3 decode, 4 = the whole run() on the
  * library's stream, state reset included).  Returns launches counted. */

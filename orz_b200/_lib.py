@@ -36,6 +36,7 @@ SYMBOLS = [
     "orz_encode_bound", "orz_encode_stream", "orz_decode_stream", "orz_encode_batch", "orz_decode_batch",
     "orz_batch_create", "orz_batch_free", "orz_batch_upload", "orz_batch_run", "orz_batch_result_len",
     "orz_batch_download", "orz_batch_result_dev", "orz_batch_timing",
+    "orz_segmented_bound", "orz_encode_segmented", "orz_segmented_raw_len", "orz_decode_segmented",
 ]
 
 _lib = None
@@ -80,6 +81,11 @@ def load():
     L.orz_batch_result_dev.argtypes = [vp, C.c_int]
     L.orz_batch_result_dev.restype = vp
     L.orz_batch_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.orz_segmented_bound.argtypes = [sz, sz]
+    L.orz_segmented_bound.restype = sz
+    L.orz_encode_segmented.argtypes = [C.c_int, C.POINTER(LZCfg), C.c_int, vp, sz, sz, vp, sz, szp]
+    L.orz_segmented_raw_len.argtypes = [vp, sz, szp]
+    L.orz_decode_segmented.argtypes = [C.c_int, vp, sz, vp, sz, szp]
     _lib = L
     return L
 

@@ -20,7 +20,7 @@ static bool read_all(FILE *f, std::vector<uint8_t> &buf) {
 
 static int usage() {
     fprintf(stderr, "orz: an optimized ROLZ data compressor (B200 build)\n\n"
-                    "Usage: orz encode [-s|--silent] [-l|--level <0..2>] [IPATH] [OPATH]\n"
+                    "Usage: orz encode [-s|--silent] [-l|--level <0..2>] [--segment-size BYTES] [IPATH] [OPATH]\n"
                     "       orz decode [-s|--silent] [IPATH] [OPATH]\n");
     return 2;
 }
@@ -32,6 +32,7 @@ int main(int argc, char **argv) {
     const bool enc = cmd == "encode";
     bool silent = false;
     int level = 2; // main.rs:30 default_value = "2"
+    size_t segment_size = 0; // extension: > 0 writes the segment container of include/orz_b200.h instead of one orz stream
     std::vector<const char *> paths;
     for (int i = 2; i < argc; i++) {
         const std::string a = argv[i];
@@ -39,6 +40,9 @@ int main(int argc, char **argv) {
         else if (enc && (a == "-l" || a == "--level")) {
             if (++i >= argc) return usage();
             level = atoi(argv[i]);
+        } else if (enc && a == "--segment-size") {
+            if (++i >= argc) return usage();
+            segment_size = (size_t)strtoull(argv[i], nullptr, 10);
         } else if (enc && a.rfind("-l", 0) == 0 && a.size() > 2) level = atoi(a.c_str() + 2);
         else if (enc && a.rfind("--level=", 0) == 0) level = atoi(a.c_str() + 8);
         else if (a == "-h" || a == "--help") return usage(), 0;
@@ -67,9 +71,16 @@ int main(int argc, char **argv) {
     std::vector<uint8_t> out;
     size_t out_len = 0;
     int rc;
-    if (enc) {
+    size_t raw_len = 0;
+    if (enc && segment_size > 0) {
+        out.resize(orz_segmented_bound(in.size(), segment_size));
+        rc = orz_encode_segmented(0, &cfg, level, in.data(), in.size(), segment_size, out.data(), out.size(), &out_len);
+    } else if (enc) {
         out.resize(orz_encode_bound(in.size()));
         rc = orz_encode_stream(0, &cfg, in.data(), in.size(), out.data(), out.size(), &out_len);
+    } else if (orz_segmented_raw_len(in.data(), in.size(), &raw_len) == ORZ_OK) { // "ORZS" container
+        out.resize(raw_len + 1);
+        rc = orz_decode_segmented(0, in.data(), in.size(), out.data(), raw_len, &out_len);
     } else {
         size_t cap = in.size() * 8 + (1 << 20);
         for (;;) { // the orz stream carries no size field: grow until it fits

@@ -77,6 +77,45 @@ def decode_batch(targets, out_caps=None, device: int = 0):
     return [outs[i][: outl[i]].tobytes() for i in range(n)]
 
 
+def encode_segmented(source, segment_size: int = 1 << 24, cfg=2, device: int = 0) -> bytes:
+    """Segment container (extension, include/orz_b200.h): independent orz streams of `segment_size` bytes + index + CRC32."""
+    L = load()
+    level = int(cfg) if not isinstance(cfg, LZCfg) else 255
+    cfg = _cfg(cfg)
+    a = _u8(source)
+    cap = L.orz_segmented_bound(a.size, segment_size)
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_size_t()
+    check(L.orz_encode_segmented(device, C.byref(cfg), level, a.ctypes.data if a.size else None, a.size, segment_size,
+                                 out.ctypes.data, cap, C.byref(n)), "encoding failed")
+    return out[: n.value].tobytes()
+
+
+def decode_segmented(target, device: int = 0) -> bytes:
+    L = load()
+    a = _u8(target)
+    raw = C.c_size_t()
+    check(L.orz_segmented_raw_len(a.ctypes.data, a.size, C.byref(raw)), "decoding failed")
+    out = np.empty(max(raw.value, 1), dtype=np.uint8)
+    n = C.c_size_t()
+    check(L.orz_decode_segmented(device, a.ctypes.data, a.size, out.ctypes.data, raw.value, C.byref(n)), "decoding failed")
+    return out[: n.value].tobytes()
+
+
+def segment_streams(container) -> list:
+    """The independent orz streams inside a container (each decodable by the reference `orz decode`)."""
+    b = bytes(container)
+    assert b[:4] == b"ORZS" and b[4] == 1
+    nseg = int.from_bytes(b[20:24], "little")
+    pos = 24 + 12 * nseg
+    out = []
+    for i in range(nseg):
+        cl = int.from_bytes(b[24 + 12 * i + 4:24 + 12 * i + 8], "little")
+        out.append(b[pos:pos + cl])
+        pos += cl
+    return out
+
+
 class Batch:
     """Device-resident batch (include/orz_b200.h orz_batch_*): upload once, run() touches only HBM."""
     ENCODE, DECODE = 0, 1

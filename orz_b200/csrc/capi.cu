@@ -551,6 +551,124 @@ extern "C" int orz_decode_stream(int device, const uint8_t *in, size_t n, uint8_
 }
 
 // ------------------------------------------------------------------------------------------------
+// segment container (extension): independent orz streams + index + CRC32
+// ------------------------------------------------------------------------------------------------
+static uint32_t crc32_ieee(const uint8_t *p, size_t n) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        init = true;
+    }
+    uint32_t c = 0xffffffffu;
+    for (size_t i = 0; i < n; i++) c = table[(c ^ p[i]) & 0xffu] ^ (c >> 8);
+    return c ^ 0xffffffffu;
+}
+static void put32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
+static void put64(uint8_t *p, uint64_t v) { memcpy(p, &v, 8); }
+static uint32_t get32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static uint64_t get64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+static const size_t kSegHdr = 24, kSegEnt = 12;
+
+extern "C" size_t orz_segmented_bound(size_t n, size_t segment_size) {
+    if (segment_size == 0) return 0;
+    const size_t nseg = (n + segment_size - 1) / segment_size;
+    return kSegHdr + nseg * kSegEnt + nseg * orz_encode_bound(segment_size < n ? segment_size : n) + 16;
+}
+
+extern "C" int orz_encode_segmented(int device, const orz_lzcfg *cfg, int level_tag, const uint8_t *in, size_t n, size_t segment_size,
+                                    uint8_t *out, size_t out_cap, size_t *out_len) {
+    if (!cfg || (n && !in) || !out || !out_len || segment_size == 0 || segment_size > 0xffffffffull) return ORZ_EARG;
+    const size_t nseg = (n + segment_size - 1) / segment_size;
+    if (nseg > 0x7fffffffull) return ORZ_EARG;
+    const size_t table_end = kSegHdr + nseg * kSegEnt;
+    if (out_cap < table_end) return ORZ_ENOSPC;
+    memcpy(out, "ORZS", 4);
+    out[4] = 1;
+    out[5] = (uint8_t)level_tag;
+    out[6] = out[7] = 0;
+    put64(out + 8, n);
+    put32(out + 16, (uint32_t)segment_size);
+    put32(out + 20, (uint32_t)nseg);
+    if (nseg == 0) {
+        *out_len = table_end;
+        return ORZ_OK;
+    }
+    std::vector<const uint8_t *> ins(nseg);
+    std::vector<size_t> lens(nseg), caps(nseg), got(nseg);
+    std::vector<std::vector<uint8_t>> tmp(nseg);
+    std::vector<uint8_t *> outs(nseg);
+    for (size_t i = 0; i < nseg; i++) {
+        ins[i] = in + i * segment_size;
+        lens[i] = (i + 1 < nseg) ? segment_size : n - i * segment_size;
+        caps[i] = orz_encode_bound(lens[i]);
+        tmp[i].resize(caps[i]);
+        outs[i] = tmp[i].data();
+    }
+    const int rc = orz_encode_batch(device, cfg, (int)nseg, ins.data(), lens.data(), outs.data(), caps.data(), got.data());
+    if (rc != ORZ_OK) return rc;
+    size_t pos = table_end;
+    for (size_t i = 0; i < nseg; i++) {
+        if (pos + got[i] > out_cap) return ORZ_ENOSPC;
+        uint8_t *ent = out + kSegHdr + i * kSegEnt;
+        put32(ent, (uint32_t)lens[i]);
+        put32(ent + 4, (uint32_t)got[i]);
+        put32(ent + 8, crc32_ieee(ins[i], lens[i]));
+        memcpy(out + pos, outs[i], got[i]);
+        pos += got[i];
+    }
+    *out_len = pos;
+    return ORZ_OK;
+}
+
+extern "C" int orz_segmented_raw_len(const uint8_t *in, size_t n, size_t *raw_len) {
+    if (!in || !raw_len || n < kSegHdr || memcmp(in, "ORZS", 4) != 0 || in[4] != 1) return ORZ_EINVAL;
+    *raw_len = (size_t)get64(in + 8);
+    return ORZ_OK;
+}
+
+extern "C" int orz_decode_segmented(int device, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *out_len) {
+    size_t raw = 0;
+    if (!out_len || orz_segmented_raw_len(in, n, &raw) != ORZ_OK) return ORZ_EINVAL;
+    const size_t seg_size = get32(in + 16), nseg = get32(in + 20);
+    const size_t table_end = kSegHdr + nseg * kSegEnt;
+    if (table_end > n || (nseg && seg_size == 0) || raw > nseg * (uint64_t)seg_size) return ORZ_EINVAL;
+    if (raw > out_cap) return ORZ_ENOSPC;
+    if (nseg == 0) {
+        *out_len = 0;
+        return raw == 0 ? ORZ_OK : ORZ_EINVAL;
+    }
+    std::vector<const uint8_t *> ins(nseg);
+    std::vector<size_t> lens(nseg), caps(nseg), got(nseg);
+    std::vector<uint8_t *> outs(nseg);
+    size_t pos = table_end, opos = 0;
+    for (size_t i = 0; i < nseg; i++) {
+        const uint8_t *ent = in + kSegHdr + i * kSegEnt;
+        const size_t rl = get32(ent), cl = get32(ent + 4);
+        if (rl > seg_size || pos + cl > n || opos + rl > raw) return ORZ_EINVAL;
+        ins[i] = in + pos;
+        lens[i] = cl;
+        outs[i] = out + opos;
+        caps[i] = rl;
+        pos += cl;
+        opos += rl;
+    }
+    if (opos != raw) return ORZ_EINVAL;
+    const int rc = orz_decode_batch(device, (int)nseg, ins.data(), lens.data(), outs.data(), caps.data(), got.data());
+    if (rc != ORZ_OK) return rc == ORZ_ENOSPC ? ORZ_EINVAL : rc; // a segment larger than its index entry is a corrupt container
+    for (size_t i = 0; i < nseg; i++) {
+        const uint8_t *ent = in + kSegHdr + i * kSegEnt;
+        if (got[i] != caps[i] || crc32_ieee(outs[i], got[i]) != get32(ent + 8)) return ORZ_EINVAL;
+    }
+    *out_len = raw;
+    return ORZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // operator interface (lz.rs:75-95, 353-366): host drives chunks, codec state stays in HBM
 // ------------------------------------------------------------------------------------------------
 struct orz_lzenc {

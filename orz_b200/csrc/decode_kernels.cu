@@ -60,10 +60,12 @@ __device__ __forceinline__ SymRank *rank_table(SymRank *symranks, SymRank *cache
 struct BitReader { // coder.rs:91-157,159-196
     const uint8_t *base; // 4 B aligned
     uint64_t pos;        // byte offset of the next refill
+    uint64_t lim;        // reads are clamped to this offset (end of the input; the allocation is padded past it)
     uint64_t bb;
     int bl;
     __device__ __forceinline__ void refill() {
         if (bl < 32) {
+            if (pos > lim) pos = lim; // a malformed header must not walk the reader out of the buffer (coder.rs:152-156 over-reads <= 4 B)
             const uint32_t *wp = reinterpret_cast<const uint32_t *>(base + (pos & ~3ull));
             const uint32_t w = bswap32(__funnelshift_r(wp[0], wp[1], ((uint32_t)pos & 3u) * 8u));
             bb = (bb << 32) | w;
@@ -270,6 +272,7 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
         BitReader br;
         br.base = in;
         br.pos = self_driven ? in_pos : 0;
+        br.lim = in_len; // in stream mode in_pos + t <= in_len was checked above
         br.bb = 0;
         br.bl = 0;
         uint32_t sbuf_len = 0, n_items = 0;

@@ -46,3 +46,14 @@ def test_cli_round_trip_matches_oracle(tmp_path):
     assert r.returncode == 0 and b"statistics:" in r.stderr and enc.read_bytes() == pyoracle.encode(data, 2)
     r = _run(["decode", "-s"], enc.read_bytes())  # stdin -> stdout
     assert r.returncode == 0 and r.stdout == data
+
+
+@pytest.mark.gpu
+def test_cli_segment_container(tmp_path):
+    data = datagen.text_like(200_000, seed=78)
+    src = tmp_path / "in.txt"
+    src.write_bytes(data)
+    r = _run(["encode", "-s", "-l", "1", "--segment-size", "65536", str(src)])
+    assert r.returncode == 0 and r.stdout[:4] == b"ORZS"
+    r2 = _run(["decode", "-s"], r.stdout)  # the container is recognised by its magic
+    assert r2.returncode == 0 and r2.stdout == data

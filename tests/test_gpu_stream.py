@@ -117,3 +117,34 @@ def test_full_enwik8_decode_and_segment_properties():
     for s, e in zip(segs[:6], encs[:6]):
         assert e == pyoracle.encode(s, 1)
     assert [pyoracle.decode(e, len(s) + 64) for s, e in zip(segs, encs)] == segs
+
+
+def test_decoder_survives_corrupted_streams():
+    """Fuzz: flipped bytes, truncations and hostile headers must end in an error code or wrong bytes — never in a hang
+    or a device fault (the reference has undefined behaviour here, lib.rs:36-39)."""
+    rng = np.random.default_rng(1234)
+    data = datagen.text_like(60_000, seed=55)
+    comp = pyoracle.encode(data, 1)
+    variants = []
+    for _ in range(24):
+        b = bytearray(comp)
+        for _ in range(int(rng.integers(1, 6))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        variants.append(bytes(b))
+    for cut in (1, 2, 5, len(comp) // 3, len(comp) - 2):
+        variants.append(comp[:cut])
+    variants.append(b"\xfc\xff\x7f" + b"\xff" * 64)          # claims a 2 MB payload that is not there
+    variants.append(bytes([8]) + b"\xff" * 8 + b"\x00")       # tiny payload, all ones: huge varints / item counts
+    variants.append(bytes([8]) + b"\x00" * 8 + b"\x00")
+    ok = bad = 0
+    for v in variants:
+        try:
+            out = orz_b200.decode(v, out_cap=len(data) + 4096)
+            ok += 1
+            assert isinstance(out, bytes)
+        except orz_b200.OrzError as e:
+            assert e.code in (-1, -2, -3), e.code
+            bad += 1
+    assert bad >= 5  # the truncations at least
+    # the device is still healthy afterwards
+    assert orz_b200.decode(comp, out_cap=len(data) + 64) == data
