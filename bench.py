@@ -146,7 +146,7 @@ def main():
     base = {"metric": METRIC if args.direction == "encode" else "decode MB/s on the oracle-compressed corpus (BASELINE configs[4])",
             "unit": "MB/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8",
-            "data": ("real: " if "enwik8 (" in data_desc or "tiled" in data_desc else "synthetic: ") + data_desc,
+            "data": data_desc if data_desc.startswith("synthetic") else "real: " + data_desc,
             "config": config}
     if args.bytes != N_BYTES:
         base["invalid"] = "debug corpus size"
