@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liborz_b200.so")
+LIB_PATH = os.environ.get("ORZ_B200_LIB") or os.path.join(_HERE, "liborz_b200.so")  # override: A/B builds of the same ABI
 
 ORZ_OK, ORZ_EINVAL, ORZ_ENOSPC, ORZ_EEOF, ORZ_ENOMEM, ORZ_ECUDA, ORZ_EARG = 0, -1, -2, -3, -4, -5, -6
 

@@ -128,7 +128,13 @@ __device__ __forceinline__ void sts_volatile_v4(volatile void *p, uint4 v) {
 // lane 0's value for the whole warp (also reconverges the warp)
 __device__ __forceinline__ uint32_t bcast0(uint32_t v) { return __shfl_sync(kFull, v, 0); }
 
-__device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(kFull, v); } // one REDUX instruction on sm_80+
+__device__ __forceinline__ int warp_max(int v) {
+    for (int o = 16; o; o >>= 1) {
+        const int other = __shfl_xor_sync(kFull, v, o);
+        v = other > v ? other : v;
+    }
+    return v;
+}
 
 struct ProbeResult {
     int fm_len, fm_idx;
@@ -142,7 +148,7 @@ struct ProbeResult {
 // Returns false if the walk was abandoned because the parse already moved past q.
 __device__ __forceinline__ bool probe_chain(const uint8_t *win, const ENode *bn, int h0, uint32_t q, uint32_t buf_len, int depth0,
                                             int depth1, int depth2, int lane, const volatile uint32_t *s_spos, ProbeResult &R,
-                                            int &f_next, int &cand_slot, bool &single_round, long long *ph) {
+                                            int &f_next, int &cand_slot, bool &single_round) {
     R.fm_len = 0;
     R.fm_idx = 0;
     R.fm_pl = 0;
@@ -157,7 +163,6 @@ __device__ __forceinline__ bool probe_chain(const uint8_t *win, const ENode *bn,
     int x_idx = h0, my_next;
     enode_head(bn, h0, x_pl, x_exp, my_next, lane);
     f_next = my_next;
-    if (ph) { const long long t = clock64(); ph[1] += t - ph[6]; ph[6] = t; } // head record arrived
     int dmax = depth0 > depth1 ? depth0 : depth1;
     dmax = dmax > depth2 ? dmax : depth2;
     if (dmax <= 0) return true;
@@ -177,7 +182,6 @@ __device__ __forceinline__ bool probe_chain(const uint8_t *win, const ENode *bn,
         uint32_t my_pl, my_exp;
         int my_idx;
         const int nvl = gather_round(bn, lane, cap, x_pl, x_exp, x_idx, my_next, my_pl, my_exp, my_idx);
-        if (ph) { const long long t = clock64(); ph[2] += t - ph[6]; ph[6] = t; } // gather done
         const int gi = seen + lane - lo;                 // index of this lane's node in chain order
         const bool have = lane >= lo && lane < nvl;
         if (first_round) cand_slot = (lane < nvl || (lane == nvl && my_idx >= 0)) ? my_idx : -1; // include the slot the walk stopped at
@@ -185,7 +189,6 @@ __device__ __forceinline__ bool probe_chain(const uint8_t *win, const ENode *bn,
         int lcp = -1;
         if (have) lcp = lcp_win_win(win, node_pos(my_pl), q);
 
-        if (ph) { const long long t = clock64(); ph[3] += t - ph[6]; ph[6] = t; } // LCPs done
         R.max_d1 = max(R.max_d1, warp_max((have && gi < depth1) ? lcp : -1));
         R.max_d2 = max(R.max_d2, warp_max((have && gi < depth2) ? lcp : -1));
 
@@ -210,12 +213,10 @@ __device__ __forceinline__ bool probe_chain(const uint8_t *win, const ENode *bn,
                     }
                 }
                 if (u >= 32) break;
-                // lcp (<= 240), expected (<= 240) and slot (< 4094) travel in one shuffle, pos|lenmin in a second
-                const uint32_t packed = __shfl_sync(kFull, (uint32_t)lcp | my_exp << 8 | (uint32_t)my_idx << 16, u);
+                max_len = __shfl_sync(kFull, lcp, u);
+                exp_best = __shfl_sync(kFull, my_exp, u);
                 pl_best = __shfl_sync(kFull, my_pl, u);
-                max_len = (int)(packed & 0xffu);
-                exp_best = (packed >> 8) & 0xffu;
-                idx_best = (int)(packed >> 16);
+                idx_best = __shfl_sync(kFull, my_idx, u);
                 if (max_len == kMatchMax || (exp_best > 0 && max_len > (int)exp_best)) { // matcher.rs:162-167
                     fm_done = true;
                     break;
@@ -223,7 +224,6 @@ __device__ __forceinline__ bool probe_chain(const uint8_t *win, const ENode *bn,
                 cur = u;
             }
         }
-        if (ph) { const long long t = clock64(); ph[4] += t - ph[6]; ph[6] = t; } // resolved
         seen += nvl - lo;
         if (seen >= depth0) fm_done = true;
         const bool lazy_done = (seen >= depth1 || R.max_d1 >= kMatchMax / 2 + 2) && (seen >= depth2 || R.max_d2 >= kMatchMax / 2 + 2);
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                 volatile ProbePub *P = &sh.pub[spos % NS];
                 uint32_t c, ver, hc;
                 unsigned wl = 0;
-                const long long t_a = (dbg_flags & 8u) ? clock64() : 0;
+                const long long t_a = clock64();
                 for (;;) { // wait for a probe of spos built under the current version of its bucket
                     w0++;
                     if (++wl > wd_limit) {
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                     if (wl == 1) cz_stale++;
                 }
                 if (wd_code) break;
-                const long long t_b = (dbg_flags & 8u) ? clock64() : 0;
+                const long long t_b = clock64();
                 cyc_own += t_b - t_a;
                 const uint4 v1 = lds_volatile_v4(&P->fm);
                 const uint4 v2 = lds_volatile_v4(&P->e0);
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                     }
                 }
                 if (wd_code) break;
-                if (dbg_flags & 8u) cyc_lazy += clock64() - t_b;
+                cyc_lazy += clock64() - t_b;
 
                 const bool emit_match = fm_len > 0 && lazy_id == 0;
                 const uint32_t mlen = emit_match ? fm_len : 0u;
@@ -520,12 +520,12 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                 w1 = (unsigned long long)cyc_lazy;
                 w2 = (unsigned long long)(clock64() - t_start);
             }
-            if (!(dbg_flags & 96u)) {
+            if (!(dbg_flags & 32u)) {
                 S->dbg[1] += w0;
                 S->dbg[2] += w1;
                 S->dbg[3] += w2;
             }
-            if (!wd_code && !(dbg_flags & 64u)) {
+            if (!wd_code) {
                 S->dbg[6] += ((unsigned long long)cz_building << 32) | cz_other;
                 S->dbg[7] += cz_stale;
             }
@@ -537,8 +537,6 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
         uint32_t pq[2] = {kNone, kNone}, pc[2] = {0, 0}, pver[2] = {0, 0};
         unsigned long long nbuild = 0, nabort = 0;
         unsigned long long bcyc = 0, nvfail = 0, lead[4] = {0, 0, 0, 0};
-        const bool timing = (dbg_flags & 96u) != 0;
-        long long ph[7] = {0, 0, 0, 0, 0, 0, 0}; // cycles (only with ORZ_B200_DBG & 96): [0] bytes+heads, [1] head record, [2] gather, [3] LCP, [4] resolve, [5] publish; [6] = last stamp
         for (;;) {
             // Control values are read by every lane but only lane 0's copy is used (bcast0): lanes that are not
             // perfectly converged could otherwise see different values and part ways before a full-mask shuffle.
@@ -578,8 +576,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
             // ---- build the probe of q ----
             my_q = kNone;
             nbuild++;
-            const long long tb0 = timing ? clock64() : 0;
-            ph[6] = tb0;
+            const long long tb0 = clock64();
             if (lane == 0) vpub->q = kNone;
             __threadfence_block();
             const uint32_t prev4 = ld_u32_unaligned(win, q - 4); // bytes q-4 .. q-1
@@ -593,12 +590,11 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
             __threadfence_block();
             const uint32_t head = bcast0((uint32_t)v_bhead[c]);
             const int h0 = (int)bcast0((uint32_t)(int)heads[c * kHeadsStride + e0]);
-            if (timing) { const long long t = clock64(); ph[0] += t - ph[6]; ph[6] = t; }
             ProbeResult R;
             int f_next, cand_slot;
             bool single_round;
             if (!probe_chain(win, nodes + c * kNodesStride, h0, q, sbuf_len, depth0, depth1, depth2, lane, v_spos, R, f_next, cand_slot,
-                             single_round, timing ? ph : nullptr)) {
+                             single_round)) {
                 nabort++;
                 continue;
             }
@@ -659,10 +655,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
             my_q = q;
             my_c = c;
             my_ver = v0;
-            if (timing) {
-                const long long t = clock64();
-                ph[5] += t - ph[6];
-                bcyc += t - tb0;
+            bcyc += clock64() - tb0;
+            {
                 const uint32_t d = q - bcast0(*v_spos);
                 lead[d >= 0x80000000u ? 0 : (d < 3 ? 0 : (d < 8 ? 1 : (d < 16 ? 2 : 3)))]++;
             }
@@ -670,13 +664,6 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
         if (lane == 0) {
             atomicAdd(&S->dbg[4], nbuild);
             atomicAdd(&S->dbg[5], nabort + (nvfail << 32));
-            if (dbg_flags & 64u) { // per-phase build cycles replace the other counters
-                atomicAdd(&S->dbg[1], (unsigned long long)ph[0]);
-                atomicAdd(&S->dbg[2], (unsigned long long)ph[1]);
-                atomicAdd(&S->dbg[3], (unsigned long long)ph[2]);
-                atomicAdd(&S->dbg[6], (unsigned long long)ph[3]);
-                atomicAdd(&S->dbg[7], (unsigned long long)ph[4] | (unsigned long long)(ph[5] >> 8) << 40);
-            }
             if (dbg_flags & 32u) { // builder timing report replaces the executor's spin counters
                 atomicAdd(&S->dbg[1], bcyc);
                 atomicAdd(&S->dbg[2], lead[0] | lead[1] << 32);
