@@ -318,7 +318,7 @@ __device__ __forceinline__ void restamp_probe(volatile ProbePub *P, uint32_t wan
 
 // NW warps per block.  Warp 0 is the executor; warps with (warp & 3) == 0 share its SM sub-partition and stay
 // parked so that it issues alone; the other NB warps are builders (NW = 22 -> 16 builders, NW = 11 -> 8).
-template <int NW, int NB>
+template <int NW, int NB, bool STATS> // STATS: compile the counters / clock64 instrumentation in (ORZ_B200_STATS); off in production
 __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) {
     static_assert(NB == NW - 1 - (NW - 1) / 4 && NB <= kMaxBuilders, "builder count");
     EncStream *S = &streams[blockIdx.x];
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
             unsigned long long w0 = 0, w1 = 0, w2 = 0;
             unsigned cz_building = 0, cz_other = 0, cz_stale = 0;
             long long cyc_own = 0, cyc_lazy = 0;
-            const long long t_start = clock64();
+            const long long t_start = STATS ? clock64() : 0;
             // watchdog: a probe that never arrives is a protocol bug; fail the stream instead of hanging the GPU
             const unsigned wd_limit = 30000000u; // spin iterations of ONE wait (seconds); normal waits are < 100
             int wd_code = 0;
@@ -372,27 +372,27 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                 volatile ProbePub *P = &sh.pub[spos % NS];
                 uint32_t c, ver, hc;
                 unsigned wl = 0;
-                const long long t_a = clock64();
+                const long long t_a = STATS ? clock64() : 0;
                 for (;;) { // wait for a probe of spos built under the current version of its bucket
-                    w0++;
+                    if (STATS) w0++;
                     if (++wl > wd_limit) {
                         wd_code = 1;
                         break;
                     }
                     const uint4 v = lds_volatile_v4(P);
                     if (v.x != spos) {
-                        if (wl == 1) (v.x == kNone ? cz_building : cz_other)++;
+                        if (STATS && wl == 1) (v.x == kNone ? cz_building : cz_other)++;
                         continue;
                     }
                     ver = v.y;
                     hc = v.w;
                     c = v.z & 0xffu;
                     if (v_bver[c] == ver) break;
-                    if (wl == 1) cz_stale++;
+                    if (STATS && wl == 1) cz_stale++;
                 }
                 if (wd_code) break;
-                const long long t_b = clock64();
-                cyc_own += t_b - t_a;
+                const long long t_b = STATS ? clock64() : 0;
+                if (STATS) cyc_own += t_b - t_a;
                 const uint4 v1 = lds_volatile_v4(&P->fm);
                 const uint4 v2 = lds_volatile_v4(&P->e0);
                 uint4 r0 = lds_volatile_v4(&P->rec[0]);
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                     const uint32_t lazy_len2 = lazy_len1 - (uint32_t)last_word_matched;
                     wl = 0;
                     for (;;) {
-                        w1++;
+                        if (STATS) w1++;
                         if (++wl > wd_limit) {
                             wd_code = 2;
                             break;
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                     } else {
                         wl = 0;
                         for (;;) {
-                            w2++;
+                            if (STATS) w2++;
                             if (++wl > wd_limit) {
                                 wd_code = 3;
                                 break;
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                     }
                 }
                 if (wd_code) break;
-                cyc_lazy += clock64() - t_b;
+                if (STATS) cyc_lazy += clock64() - t_b;
 
                 const bool emit_match = fm_len > 0 && lazy_id == 0;
                 const uint32_t mlen = emit_match ? fm_len : 0u;
@@ -514,18 +514,18 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
             S->spos = spos;
             S->after_literal = after_literal;
             S->n_items = n_items;
-            S->dbg[0] += n_items;
-            if (dbg_flags & 8u) { // report cycles instead of spin counts
+            if (STATS) S->dbg[0] += n_items;
+            if (STATS && (dbg_flags & 8u)) { // report cycles instead of spin counts
                 w0 = (unsigned long long)cyc_own;
                 w1 = (unsigned long long)cyc_lazy;
                 w2 = (unsigned long long)(clock64() - t_start);
             }
-            if (!(dbg_flags & 32u)) {
+            if (STATS && !(dbg_flags & 32u)) {
                 S->dbg[1] += w0;
                 S->dbg[2] += w1;
                 S->dbg[3] += w2;
             }
-            if (!wd_code) {
+            if (STATS && !wd_code) {
                 S->dbg[6] += ((unsigned long long)cz_building << 32) | cz_other;
                 S->dbg[7] += cz_stale;
             }
@@ -575,8 +575,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
             uint32_t &my_q = pq[k], &my_c = pc[k], &my_ver = pver[k];
             // ---- build the probe of q ----
             my_q = kNone;
-            nbuild++;
-            const long long tb0 = clock64();
+            if (STATS) nbuild++;
+            const long long tb0 = STATS ? clock64() : 0;
             if (lane == 0) vpub->q = kNone;
             __threadfence_block();
             const uint32_t prev4 = ld_u32_unaligned(win, q - 4); // bytes q-4 .. q-1
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
             bool single_round;
             if (!probe_chain(win, nodes + c * kNodesStride, h0, q, sbuf_len, depth0, depth1, depth2, lane, v_spos, R, f_next, cand_slot,
                              single_round)) {
-                nabort++;
+                if (STATS) nabort++;
                 continue;
             }
             // words updates of the two possible outcomes (lz.rs:208,233): words[hash2(s'-3)] = bytes s'-2, s'-1
@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
             }
             __threadfence_block();
             if (bcast0(v_bver[c]) != v0) { // the bucket changed while it was being read: rebuild
-                nvfail++;
+                if (STATS) nvfail++;
                 continue;
             }
             // ---- publish ----
@@ -655,13 +655,13 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
             my_q = q;
             my_c = c;
             my_ver = v0;
-            bcyc += clock64() - tb0;
-            {
+            if (STATS) {
+                bcyc += clock64() - tb0;
                 const uint32_t d = q - bcast0(*v_spos);
                 lead[d >= 0x80000000u ? 0 : (d < 3 ? 0 : (d < 8 ? 1 : (d < 16 ? 2 : 3)))]++;
             }
         }
-        if (lane == 0) {
+        if (STATS && lane == 0) {
             atomicAdd(&S->dbg[4], nbuild);
             atomicAdd(&S->dbg[5], nabort + (nvfail << 32));
             if (dbg_flags & 32u) { // builder timing report replaces the executor's spin counters
@@ -1281,18 +1281,28 @@ __global__ void __launch_bounds__(256) orz_enc_forward_kernel(EncStream *streams
 
 size_t emit_smem_bytes() { return sizeof(EmitShared); }
 
-void launch_parse(EncStream *d_streams, int n, cudaStream_t st) {
+template <int NW, int NB, bool STATS>
+static void launch_parse_variant(EncStream *d_streams, int n, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(orz_parse_kernel<22, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseShared));
-        cudaFuncSetAttribute(orz_parse_kernel<11, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseShared));
+        cudaFuncSetAttribute(orz_parse_kernel<NW, NB, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseShared));
         attr_set = true;
     }
+    orz_parse_kernel<NW, NB, STATS><<<n, NW * 32, sizeof(ParseShared), st>>>(d_streams);
+}
+
+void launch_parse(EncStream *d_streams, int n, cudaStream_t st) {
     // few streams: 16 builders hide more latency per stream; many streams: 8 builders, more streams per SM
     const char *force = getenv("ORZ_B200_PARSE_BUILDERS");
     const int nb = force ? atoi(force) : (n <= 2 * 148 ? 16 : 8);
-    if (nb == 16) orz_parse_kernel<22, 16><<<n, 22 * 32, sizeof(ParseShared), st>>>(d_streams);
-    else orz_parse_kernel<11, 8><<<n, 11 * 32, sizeof(ParseShared), st>>>(d_streams);
+    const bool stats = getenv("ORZ_B200_STATS") != nullptr; // counters and clock64 probes only in the instrumented build
+    if (nb == 16) {
+        if (stats) launch_parse_variant<22, 16, true>(d_streams, n, st);
+        else launch_parse_variant<22, 16, false>(d_streams, n, st);
+    } else {
+        if (stats) launch_parse_variant<11, 8, true>(d_streams, n, st);
+        else launch_parse_variant<11, 8, false>(d_streams, n, st);
+    }
 }
 void launch_emit(EncStream *d_streams, int n, cudaStream_t st) {
     static bool attr_set = false;
