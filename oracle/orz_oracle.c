@@ -4,10 +4,12 @@
  * TEST INFRASTRUCTURE ONLY (see orz_oracle.h).  Plain C11, single thread per stream exactly like
  * the reference.  All file:line citations are into the richox/orz tree @29414c6.
  *
- * Parity status: PINNED by size — enwik8 compresses to exactly the sizes published in the
- * reference README.md:43-46 at -l0/-l1/-l2 (27,898,433 / 27,217,825 / 26,892,825 bytes), and
- * round-trips byte-exact.  The reference holds no golden byte vectors, so byte-level parity
- * against real `orz` output rests on that size pin plus source fidelity.
+ * Parity status: PARITY UNPINNED against real `orz` output.  The reference holds no golden byte vectors (its tests are
+ * round-trips, coder.rs:219-266 and CI) and cannot be built here (nightly Rust, un-vendored crates).  What pins this
+ * restatement: coder.rs:219-266 re-expressed, the hand-derived vectors of SURVEY App. D (reproduced), byte-exact round
+ * trips at every level, and the whole-enwik8 sizes — 27,863,045 / 27,182,097 / 26,856,813 bytes at -l0/-l1/-l2, which
+ * are 0.13 % BELOW the README's 27,898,433 / 27,217,825 / 26,892,825 (README.md:43-46; the README names tag v1.6.2,
+ * this commit is crate 1.6.1).  See DESIGN.md §1.
  */
 #include "orz_oracle.h"
 
@@ -24,12 +26,18 @@ static inline uint32_t get_u32(const uint8_t *buf, size_t pos) {
 }
 static inline void put_u32(uint8_t *buf, size_t pos, uint32_t v) { memcpy(buf + pos, &v, 4); }
 
-/* mem.rs:41-51 — LCP in 16-byte steps, capped at max_len (a multiple of 16) */
+/* mem.rs:41-51 — LCP in 16-byte steps, capped at max_len (a multiple of 16).  Two 8-byte compares per step stand in
+ * for the reference's u8x16 compare (same reads, same result), so that the CPU baseline is not handicapped. */
 static inline size_t mem_fast_common_prefix(const uint8_t *buf, size_t p1, size_t p2, size_t max_len) {
     for (size_t l = 0; l < max_len; l += 16) {
-        for (size_t k = 0; k < 16; k++) {
-            if (buf[p1 + l + k] != buf[p2 + l + k]) return l + k;
-        }
+        uint64_t a0, a1, b0, b1;
+        memcpy(&a0, buf + p1 + l, 8);
+        memcpy(&a1, buf + p1 + l + 8, 8);
+        memcpy(&b0, buf + p2 + l, 8);
+        memcpy(&b1, buf + p2 + l + 8, 8);
+        const uint64_t x0 = a0 ^ b0, x1 = a1 ^ b1;
+        if (x0) return l + ((size_t)__builtin_ctzll(x0) >> 3);
+        if (x1) return l + 8 + ((size_t)__builtin_ctzll(x1) >> 3);
     }
     return max_len;
 }
