@@ -1,8 +1,9 @@
 // encode_kernels.cu — sm_100a kernels of the ROLZ encoder.
 //
-//   orz_parse_kernel   stage A  (lz.rs:131-235): one warp owns one stream; the ROLZ parse is a serial
-//                      state machine, the lanes cooperate inside a step (parallel candidate probes + LCP,
-//                      ballot-resolved sequential semantics of matcher.rs:135-192).
+//   orz_parse_kernel   stage A  (lz.rs:131-235): one thread block owns one stream.  The ROLZ parse is a serial
+//                      state machine; builder warps speculatively gather and resolve the match candidates of the
+//                      next positions (ring snapshots -> one parallel gather per chain, ballot-resolved semantics of
+//                      matcher.rs:135-228) under per-bucket seqlocks, one executor thread takes the decisions.
 //   orz_emit_kernel    stages B-D (lz.rs:238-344): one 512-thread block per stream — per-context rank
 //                      coding (one warp per context, table in shared memory), shared-memory histograms,
 //                      length-limited canonical Huffman build, block-wide prefix scan of bit lengths and

@@ -177,3 +177,48 @@ def test_decode_rejects_garbage():
         pyoracle.decode(bytes(enc[: len(enc) // 2]), len(data) + 64)  # truncated: UnexpectedEof
     with pytest.raises(RuntimeError):
         pyoracle.decode(bytes([0xFF, 0xFF, 0xFF, 0xFF, 0x7F]) + bytes(100), 1000)  # chunk length >= 3*PREMATCH: InvalidData
+
+
+def test_chunk_level_interface_equals_stream_interface():
+    """The operator-level restatement (lz.rs:75-95) driven like lib.rs:58-92 reproduces the stream-level output."""
+    data = datagen.text_like(150_000, seed=71) + datagen.random_bytes(20_000, seed=72)
+    cfg = pyoracle.level_cfg(1)
+    enc = pyoracle.ChunkEncoder()
+    window = np.zeros(pyoracle.BLOCK_SIZE + 2 * pyoracle.SENTINEL, dtype=np.uint8)
+    src = np.frombuffer(data, dtype=np.uint8)
+    window[pyoracle.SENTINEL + pyoracle.PREMATCH: pyoracle.SENTINEL + pyoracle.PREMATCH + src.size] = src
+    out, spos = bytearray(), pyoracle.PREMATCH
+    while spos < pyoracle.PREMATCH + src.size:
+        spos, payload = enc.encode(cfg, window, pyoracle.PREMATCH + src.size, spos)
+        n, b = len(payload), bytearray()
+        while n >= 128:
+            b.append(128 + n % 128)
+            n //= 128
+        b.append(n)
+        out += bytes(b) + payload
+        pre, post = enc.last_items()
+        assert len(pre) == len(post) > 0 and (pre["ctx"] == post["ctx"]).all() and (post["symbol"] <= 388).all()
+    out += b"\x00"
+    assert bytes(out) == pyoracle.encode(data, 1)
+
+
+def test_round_trip_property_random_structures():
+    """Seeded pseudo-random structured inputs (mixtures of runs, copies and noise) round-trip at every level."""
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        parts = []
+        for _ in range(int(rng.integers(1, 12))):
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                parts.append(bytes(rng.integers(0, 256, size=int(rng.integers(1, 400)), dtype=np.uint8)))
+            elif kind == 1:
+                parts.append(bytes([int(rng.integers(0, 256))]) * int(rng.integers(1, 700)))
+            elif kind == 2 and parts:
+                src = b"".join(parts)
+                o = int(rng.integers(0, len(src)))
+                parts.append(src[o:o + int(rng.integers(1, 300))])
+            else:
+                parts.append(bytes(rng.integers(97, 123, size=int(rng.integers(1, 60)), dtype=np.uint8)) * int(rng.integers(1, 9)))
+        data = b"".join(parts)
+        level = trial % 3
+        assert pyoracle.decode(pyoracle.encode(data, level), len(data) + 64) == data
