@@ -50,6 +50,9 @@ def load():
         raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(nvcc, sm_100a). orz_b200 has no CPU fallback.")
     L = C.CDLL(LIB_PATH)
+    if hasattr(L, "orz_b200_is_emulator") and os.environ.get("ORZ_B200_TEST_EMULATOR") != "1":
+        raise ImportError(f"{LIB_PATH} is the test-tier SIMT emulator build (tests/simt/), not the sm_100a library; "
+                          "orz_b200 has no CPU fallback.")
     vp, sz, szp = C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)
     L.orz_level_cfg.argtypes = [C.c_int, C.POINTER(LZCfg)]
     L.orz_strerror.argtypes = [C.c_int]

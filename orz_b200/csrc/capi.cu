@@ -34,6 +34,12 @@ using namespace orz;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+#ifdef ORZ_SIMT_EMU
+// Only the test-tier emulator build (tests/simt/) exports this marker; orz_b200/_lib.py refuses to load a library
+// that has it unless the test suite asks for it explicitly, so the emulator can never stand in for the GPU.
+extern "C" int orz_b200_is_emulator(void) { return 1; }
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // timing: CUDA events around every launch, on the launching stream
 // ------------------------------------------------------------------------------------------------

@@ -205,7 +205,7 @@ template <int CACHE>
 __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
     DecStream *S = &streams[blockIdx.x];
     if (S->status != 0) return;
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    ORZ_DYN_SHARED(smem_raw);
     DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
     SymRank *cache = reinterpret_cast<SymRank *>(smem_raw + ((sizeof(DecShared) + 15) & ~size_t(15)));
     const int lane = threadIdx.x;
@@ -579,11 +579,11 @@ void launch_decode(DecStream *d_streams, int n, cudaStream_t st) {
     const char *force = getenv("ORZ_B200_DEC_CACHE");
     // measured in round 1: the cache does not pay (misses ~17 % of items, a swap costs as much as it saves): off by default
     const bool cached = force ? atoi(force) != 0 : false;
-    if (cached) orz_decode_kernel<128><<<n, 32, big, st>>>(d_streams);
-    else orz_decode_kernel<0><<<n, 32, base, st>>>(d_streams);
+    if (cached) ORZ_LAUNCH(orz_decode_kernel<128>, n, 32, big, st, d_streams);
+    else ORZ_LAUNCH(orz_decode_kernel<0>, n, 32, base, st, d_streams);
 }
 void launch_dec_forward(DecStream *d_stream, uint32_t forward_len, cudaStream_t st) {
-    orz_dec_forward_kernel<<<148, 256, 0, st>>>(d_stream, forward_len);
+    ORZ_LAUNCH(orz_dec_forward_kernel, 148, 256, 0, st, d_stream, forward_len);
 }
 
 } // namespace orz

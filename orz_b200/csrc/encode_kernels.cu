@@ -122,6 +122,10 @@ __device__ __forceinline__ int gather_round(const ENode *bn, int lane, int cap, 
 }
 
 __device__ __forceinline__ void sts_volatile_v4(volatile void *p, uint4 v) {
+#ifdef ORZ_SIMT_EMU
+    *reinterpret_cast<uint4 *>(const_cast<void *>(p)) = v;
+    return;
+#endif
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(const_cast<void *>(p));
     asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -271,6 +275,11 @@ constexpr int kMaxBuilders = 16;
 // one 16-byte volatile read of shared memory (the executor's poll)
 __device__ __forceinline__ uint4 lds_volatile_v4(const volatile void *p) {
     uint4 v;
+#ifdef ORZ_SIMT_EMU
+    ORZ_POLL();
+    v = *reinterpret_cast<const uint4 *>(const_cast<const void *>(p));
+    return v;
+#endif
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(const_cast<void *>(p));
     asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
     return v;
@@ -324,7 +333,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
     static_assert(NB == NW - 1 - (NW - 1) / 4 && NB <= kMaxBuilders, "builder count");
     EncStream *S = &streams[blockIdx.x];
     if (S->status != 0) return;
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    ORZ_DYN_SHARED(smem_raw);
     ParseShared &sh = *reinterpret_cast<ParseShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NT = NW * 32;
@@ -888,7 +897,7 @@ struct EmitShared {
 __global__ void __launch_bounds__(kEmitThreads) orz_emit_kernel(EncStream *streams) {
     EncStream *S = &streams[blockIdx.x];
     if (S->status != 0) return;
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    ORZ_DYN_SHARED(smem_raw);
     EmitShared &sh = *reinterpret_cast<EmitShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Item *items = S->items;
@@ -1017,16 +1026,23 @@ __global__ void __launch_bounds__(kEmitThreads) orz_emit_kernel(EncStream *strea
                     uint32_t next_i = i > sub ? i - sub : 0;
                     if (next_i < (i >> 1)) next_i = i >> 1;
                     const uint32_t d = i - next_i;
+                    // Every lane replays the same update on the shared table.  All reads come first, then a warp
+                    // barrier, then the writes: no lane may see the table half-rewritten by a faster lane.
+                    const uint32_t ni2 = next_i, ni1 = next_i + d / 2;
+                    uint16_t nv1 = 0, nv2 = 0;
                     if (d == 1) {
-                        const uint16_t nv1 = tab.value[next_i];
+                        nv1 = tab.value[next_i];
+                    } else if (d > 1) {
+                        nv1 = tab.value[ni1];
+                        nv2 = tab.value[ni2];
+                    }
+                    __syncwarp();
+                    if (d == 1) {
                         tab.index[v] = (uint16_t)next_i;
                         tab.value[i] = nv1;
                         tab.index[nv1] = (uint16_t)i;
                         tab.value[next_i] = (uint16_t)v;
                     } else if (d > 1) {
-                        const uint32_t ni2 = next_i, ni1 = next_i + d / 2;
-                        const uint16_t nv1 = tab.value[ni1];
-                        const uint16_t nv2 = tab.value[ni2];
                         tab.value[i] = nv1;
                         tab.index[nv1] = (uint16_t)i;
                         tab.value[ni1] = nv2;
@@ -1289,7 +1305,8 @@ static void launch_parse_variant(EncStream *d_streams, int n, cudaStream_t st) {
         cudaFuncSetAttribute(orz_parse_kernel<NW, NB, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseShared));
         attr_set = true;
     }
-    orz_parse_kernel<NW, NB, STATS><<<n, NW * 32, sizeof(ParseShared), st>>>(d_streams);
+    auto kern = orz_parse_kernel<NW, NB, STATS>;
+    ORZ_LAUNCH(kern, n, NW * 32, sizeof(ParseShared), st, d_streams);
 }
 
 void launch_parse(EncStream *d_streams, int n, cudaStream_t st) {
@@ -1311,12 +1328,12 @@ void launch_emit(EncStream *d_streams, int n, cudaStream_t st) {
         cudaFuncSetAttribute(orz_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared));
         attr_set = true;
     }
-    orz_emit_kernel<<<n, kEmitThreads, sizeof(EmitShared), st>>>(d_streams);
+    ORZ_LAUNCH(orz_emit_kernel, n, kEmitThreads, sizeof(EmitShared), st, d_streams);
 }
-void launch_enc_begin(EncStream *d_streams, int n, cudaStream_t st) { orz_enc_begin_kernel<<<n, 256, 0, st>>>(d_streams); }
+void launch_enc_begin(EncStream *d_streams, int n, cudaStream_t st) { ORZ_LAUNCH(orz_enc_begin_kernel, n, 256, 0, st, d_streams); }
 void launch_enc_forward(EncStream *d_stream, uint32_t forward_len, cudaStream_t st) {
-    orz_enc_forward_kernel<<<148, 256, 0, st>>>(d_stream, forward_len, 0);
-    orz_enc_forward_kernel<<<148, 256, 0, st>>>(d_stream, forward_len, 1);
+    ORZ_LAUNCH(orz_enc_forward_kernel, 148, 256, 0, st, d_stream, forward_len, 0);
+    ORZ_LAUNCH(orz_enc_forward_kernel, 148, 256, 0, st, d_stream, forward_len, 1);
 }
 
 } // namespace orz

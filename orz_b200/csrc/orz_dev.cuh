@@ -6,7 +6,21 @@
 // (matcher.rs:28-31,102-105) are fused into one 8-byte record so that one chain hop is one load.
 #pragma once
 #include <cstdint>
+#ifdef ORZ_SIMT_EMU
+// Test tier only: tests/simt/ compiles these same sources for the host-side SIMT emulator (fibres instead of
+// CUDA threads) so that the CPU-only tests can execute the kernel source against the oracle.  The product
+// library is always built by nvcc without this macro.
+#include "simt_rt.h"
+#define ORZ_LAUNCH(kern, grid, block, smem, st, ...) simt::launch(dim3(grid), dim3(block), (smem), [=]() { kern(__VA_ARGS__); })
+#define ORZ_COST(c) simt::cost(c)   // virtual-clock annotation at a dependent load (latency model, SIMT_VT=1)
+#define ORZ_POLL() simt::poll()     // a spin-loop iteration: let the other fibres run
+#else
 #include <cuda_runtime.h>
+#define ORZ_DYN_SHARED(name) extern __shared__ __align__(16) uint8_t name[]
+#define ORZ_LAUNCH(kern, grid, block, smem, st, ...) kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__)
+#define ORZ_COST(c) ((void)0)
+#define ORZ_POLL() ((void)0)
+#endif
 
 namespace orz {
 

@@ -1,0 +1,90 @@
+"""CPU tier: the encoder's CUDA kernel SOURCE executed by the SIMT emulator (tests/simt/) against the oracle.
+
+The emulator compiles orz_b200/csrc/*.cu as host C++ (-DORZ_SIMT_EMU): every CUDA thread is a fibre, warp
+collectives and block barriers block until all named lanes arrive, the seqlock / probe-mailbox protocols of stage A
+run for real.  It checks the kernel logic bit for bit without a GPU and, with SIMT_SEED, under randomised
+interleavings of the warps.  It is test infrastructure: the product loader refuses the emulator build
+(test_loader_refuses_the_emulator_build), and the `-m gpu` tests remain the parity tests proper.
+
+The decoder kernel is not emulated: it runs its serial chain redundantly on all 32 lanes of one converged warp
+(lock step is part of its design), which a fibre-per-lane model cannot reproduce.
+"""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from oracle import pyoracle
+from tests import datagen
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIMT = os.path.join(ROOT, "tests", "simt")
+EMU_LIB = os.path.join(SIMT, "liborz_b200_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-C", SIMT, "liborz_b200_emu.so"], stdout=subprocess.DEVNULL)
+    return EMU_LIB
+
+
+def _run(emu, spec, env_extra=None, timeout=600):
+    env = dict(os.environ, ORZ_B200_LIB=emu, ORZ_B200_TEST_EMULATOR="1", SIMT_SWITCH_LIMIT="20000000000")
+    env.update(env_extra or {})
+    out = subprocess.run([sys.executable, os.path.join(SIMT, "run_case.py"), json.dumps(spec)], env=env, capture_output=True,
+                         text=True, timeout=timeout)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def _want(data, level):
+    enc = pyoracle.encode(data, level)
+    return {"len": len(enc), "sha256": hashlib.sha256(enc).hexdigest()}
+
+
+def _data(c):
+    return bytes.fromhex(c["literal"]) if "literal" in c else getattr(datagen, c["gen"])(c["n"], seed=c.get("seed", 1))
+
+
+TINY = [b"", b"a", b"abcd", b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa", b"the quick brown fox jumps over the lazy dog. " * 30]
+
+
+@pytest.mark.parametrize("level", [0, 2])
+def test_emulated_kernels_match_oracle_tiny(emu, level):
+    cases = [{"literal": d.hex()} for d in TINY]
+    got = _run(emu, {"level": level, "cases": cases, "batch": True})
+    assert got == [_want(d, level) for d in TINY]
+
+
+@pytest.mark.parametrize("level,case", [(2, {"gen": "text_like", "n": 60000, "seed": 11}),
+                                        (1, {"gen": "low_entropy", "n": 50000, "seed": 12}),
+                                        (0, {"gen": "random_bytes", "n": 12000, "seed": 13})])
+def test_emulated_kernels_match_oracle(emu, level, case):
+    got = _run(emu, {"level": level, "cases": [case]})
+    assert got == [_want(_data(case), level)]
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_emulated_kernels_under_random_interleavings(emu, seed):
+    """Seeded random scheduling of the fibres: the stage A protocol (probe mailbox, per-bucket seqlocks, re-stamping)
+    must produce the same bytes under every interleaving."""
+    case = {"gen": "text_like", "n": 20000, "seed": 20 + seed}
+    got = _run(emu, {"level": 2, "cases": [case]}, {"SIMT_SEED": str(seed)})
+    assert got == [_want(_data(case), 2)]
+
+
+def test_emulated_eight_builder_variant(emu):
+    case = {"gen": "text_like", "n": 20000, "seed": 31}
+    got = _run(emu, {"level": 2, "cases": [case]}, {"ORZ_B200_PARSE_BUILDERS": "8"})
+    assert got == [_want(_data(case), 2)]
+
+
+def test_loader_refuses_the_emulator_build(emu):
+    env = dict(os.environ, ORZ_B200_LIB=emu)
+    env.pop("ORZ_B200_TEST_EMULATOR", None)
+    out = subprocess.run([sys.executable, "-c", "import orz_b200; orz_b200.device_count()"], env=env, cwd=ROOT, capture_output=True,
+                         text=True)
+    assert out.returncode != 0 and "no CPU fallback" in out.stderr
