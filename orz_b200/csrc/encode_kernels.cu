@@ -687,6 +687,10 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
     for (int i = tid; i < kNumBuckets; i += NT) S->bhead[i] = sh.bhead[i];
 }
 
+} // namespace orz
+#include "parse_v4.cuh"
+namespace orz {
+
 // LZEncoder::forward (lz.rs:82-87) in two grid-stride phases.
 // Phase 1 — Bucket::forward (matcher.rs:82-87): rebase every position, saturating at 0.
 __device__ __forceinline__ void enc_forward_rebase(ENode *nodes, uint32_t forward_len, int gid, int gsz) {
@@ -1309,7 +1313,37 @@ static void launch_parse_variant(EncStream *d_streams, int n, cudaStream_t st) {
     ORZ_LAUNCH(kern, n, NW * 32, sizeof(ParseShared), st, d_streams);
 }
 
+template <int NW, int SL, bool STATS>
+static void launch_parse4_variant(EncStream *d_streams, int n, cudaStream_t st) {
+    typedef ParseShared4<NW - 1, SL> Sh;
+    static bool attr_set = false;
+    auto kern = orz_parse4_kernel<NW, SL, STATS>;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sh));
+        attr_set = true;
+    }
+    ORZ_LAUNCH(kern, n, NW * 32, sizeof(Sh), st, d_streams);
+}
+
 void launch_parse(EncStream *d_streams, int n, cudaStream_t st) {
+    // ORZ_B200_PARSE=4: windowed warp resolver + lock-free builders (parse_v4.cuh); default: v3
+    const char *ver = getenv("ORZ_B200_PARSE");
+    if (ver && atoi(ver) == 4) {
+        const char *w = getenv("ORZ_B200_PARSE_WARPS");
+        const int nw = w ? atoi(w) : 32;
+        const bool stats4 = getenv("ORZ_B200_STATS") != nullptr;
+        if (nw == 16) {
+            if (stats4) launch_parse4_variant<16, 4, true>(d_streams, n, st);
+            else launch_parse4_variant<16, 4, false>(d_streams, n, st);
+        } else if (nw == 8) {
+            if (stats4) launch_parse4_variant<8, 4, true>(d_streams, n, st);
+            else launch_parse4_variant<8, 4, false>(d_streams, n, st);
+        } else {
+            if (stats4) launch_parse4_variant<32, 4, true>(d_streams, n, st);
+            else launch_parse4_variant<32, 4, false>(d_streams, n, st);
+        }
+        return;
+    }
     // few streams: 16 builders hide more latency per stream; many streams: 8 builders, more streams per SM
     const char *force = getenv("ORZ_B200_PARSE_BUILDERS");
     const int nb = force ? atoi(force) : (n <= 2 * 148 ? 16 : 8);

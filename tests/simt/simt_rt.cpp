@@ -150,6 +150,7 @@ inline Fiber *pop() {
 
 inline void switch_to(Fiber *next) {
     Fiber *prev = g_cur;
+    if (next == prev) return; // (random / virtual-time order can pick the fibre that just yielded)
     g_cur = next;
     cur = &next->ctx;
     g_switches++;
