@@ -322,11 +322,14 @@ def main():
     p_launch = sum(parse_launches) / len(parse_launches)
     alg_bytes = total_in + comp_bytes  # encode = N_in read + N_out written
     achieved = alg_bytes / (p_ms / 1e3) / 1e9
+    # stage A kernel of this run (mirrors launch_parse in encode_kernels.cu): one stream -> v4, several -> v3
+    parse_ver = int(os.environ.get("ORZ_B200_PARSE", "4" if n == 1 else "3"))
+    parse_kernel = "orz_parse4_kernel" if parse_ver == 4 else "orz_parse_kernel"
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("orz_parse_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get(parse_kernel + "_dram_bytes_per_launch")  # null until that kernel has an ncu capture
         except Exception:
             traffic = None
     out = dict(base)
@@ -337,7 +340,7 @@ def main():
                 "d2h_bytes_per_step": out_all},
         "gpu_launches": int(sum(launches)),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "orz_decode_kernel" if decode_dir else "orz_parse_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "orz_decode_kernel" if decode_dir else parse_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes / p_launch, "launches_per_step": p_launch,
                      "avg_launch_ms": p_ms / p_launch,

@@ -22,8 +22,13 @@ extern "C" {
 #endif
 
 /* src/lib.rs:31-34, 54-55 ; src/lz.rs:24-29 ; src/matcher.rs:18 */
+#ifdef ORZ_TEST_BLOCK_BITS /* scale model for the emulator tests (tests/simt/Makefile); never set for liborz_oracle.so */
+#define ORZ_LZ_BLOCK_SIZE        ((1u << ORZ_TEST_BLOCK_BITS) - 1)
+#define ORZ_LZ_CHUNK_SIZE        (ORZ_TEST_CHUNK_ITEMS)
+#else
 #define ORZ_LZ_BLOCK_SIZE        ((1u << 25) - 1)
 #define ORZ_LZ_CHUNK_SIZE        (1u << 20)
+#endif
 #define ORZ_LZ_MATCH_MAX_LEN     240
 #define ORZ_LZ_MATCH_MIN_LEN     4
 #define ORZ_SENTINEL_LEN         (ORZ_LZ_MATCH_MAX_LEN * 2)

@@ -1326,21 +1326,24 @@ static void launch_parse4_variant(EncStream *d_streams, int n, cudaStream_t st) 
 }
 
 void launch_parse(EncStream *d_streams, int n, cudaStream_t st) {
-    // ORZ_B200_PARSE=4: windowed warp resolver + lock-free builders (parse_v4.cuh); default: v3
+    // One stream: v4 (parse_v4.cuh: windowed warp resolver + lock-free builders; measured on a B200, enwik8 -l2:
+    // 5.56 MB/s with 16 warps, 4.59 with 32, v3 4.18).  Several streams: v3, whose many-stream behaviour is the
+    // measured one.  ORZ_B200_PARSE=3|4 forces a version, ORZ_B200_PARSE_WARPS=8|16|32 the v4 block size.
     const char *ver = getenv("ORZ_B200_PARSE");
-    if (ver && atoi(ver) == 4) {
+    const int pv = ver ? atoi(ver) : (n == 1 ? 4 : 3);
+    if (pv == 4) {
         const char *w = getenv("ORZ_B200_PARSE_WARPS");
-        const int nw = w ? atoi(w) : 32;
+        const int nw = w ? atoi(w) : 16;
         const bool stats4 = getenv("ORZ_B200_STATS") != nullptr;
-        if (nw == 16) {
-            if (stats4) launch_parse4_variant<16, 4, true>(d_streams, n, st);
-            else launch_parse4_variant<16, 4, false>(d_streams, n, st);
+        if (nw == 32) {
+            if (stats4) launch_parse4_variant<32, 4, true>(d_streams, n, st);
+            else launch_parse4_variant<32, 4, false>(d_streams, n, st);
         } else if (nw == 8) {
             if (stats4) launch_parse4_variant<8, 4, true>(d_streams, n, st);
             else launch_parse4_variant<8, 4, false>(d_streams, n, st);
         } else {
-            if (stats4) launch_parse4_variant<32, 4, true>(d_streams, n, st);
-            else launch_parse4_variant<32, 4, false>(d_streams, n, st);
+            if (stats4) launch_parse4_variant<16, 4, true>(d_streams, n, st);
+            else launch_parse4_variant<16, 4, false>(d_streams, n, st);
         }
         return;
     }

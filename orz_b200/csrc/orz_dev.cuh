@@ -25,8 +25,15 @@
 namespace orz {
 
 // ---- wire-format / algorithm constants -------------------------------------------------------
+#if defined(ORZ_SIMT_EMU) && defined(ORZ_TEST_BLOCK_BITS)
+// Emulator-only scale model (tests/simt/): small blocks and chunks so that the CPU tier reaches block slides,
+// `forward` and chunk cuts within kilobytes.  The oracle is built with the same two values for those tests.
+constexpr uint32_t kBlockSize = (1u << ORZ_TEST_BLOCK_BITS) - 1;
+constexpr uint32_t kChunkItems = ORZ_TEST_CHUNK_ITEMS;
+#else
 constexpr uint32_t kBlockSize = (1u << 25) - 1;        // lib.rs:31  LZ_BLOCK_SIZE
 constexpr uint32_t kChunkItems = 1u << 20;             // lib.rs:32  LZ_CHUNK_SIZE
+#endif
 constexpr int kMatchMax = 240;                         // lib.rs:33
 constexpr int kMatchMin = 4;                           // lib.rs:34
 constexpr uint32_t kSentinel = 480;                    // lib.rs:54

@@ -24,7 +24,9 @@ def main():
             datas.append(bytes.fromhex(c["literal"]))
         else:
             datas.append(getattr(datagen, c["gen"])(c["n"], seed=c.get("seed", 1)))
-    if spec.get("batch"):
+    if spec.get("operators"):  # LZEncoder::{new,encode,forward} driven chunk by chunk from the host (lz.rs:75-95)
+        outs = [orz_b200.encode_with_operators(d, spec["level"]) for d in datas]
+    elif spec.get("batch"):
         outs = orz_b200.encode_batch(datas, spec["level"])
     else:
         outs = [orz_b200.encode(d, spec["level"]) for d in datas]

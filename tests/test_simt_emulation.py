@@ -76,10 +76,67 @@ def test_emulated_kernels_under_random_interleavings(emu, seed):
     assert got == [_want(_data(case), 2)]
 
 
-def test_emulated_eight_builder_variant(emu):
+def test_emulated_v3_variants(emu):
+    """v3 (single-thread executor, per-bucket seqlocks) is the many-stream default; force it for one stream too."""
     case = {"gen": "text_like", "n": 20000, "seed": 31}
-    got = _run(emu, {"level": 2, "cases": [case]}, {"ORZ_B200_PARSE_BUILDERS": "8"})
+    got = _run(emu, {"level": 2, "cases": [case]}, {"ORZ_B200_PARSE": "3", "ORZ_B200_PARSE_BUILDERS": "8"})
     assert got == [_want(_data(case), 2)]
+    got = _run(emu, {"level": 2, "cases": [case]}, {"ORZ_B200_PARSE": "3"})
+    assert got == [_want(_data(case), 2)]
+
+
+@pytest.mark.parametrize("parse", ["4:32", "4:16", "4:8"])
+def test_emulated_parse_v4_matches_oracle(emu, parse):
+    """Stage A v4 (windowed warp resolver, lock-free builders; parse_v4.cuh) forced for a batch, 32/16/8-warp blocks."""
+    ver, _, warps = parse.partition(":")
+    env = {"ORZ_B200_PARSE": ver}
+    if warps:
+        env["ORZ_B200_PARSE_WARPS"] = warps
+    cases = [{"gen": "text_like", "n": 30000, "seed": 51}, {"gen": "low_entropy", "n": 30000, "seed": 52}]
+    got = _run(emu, {"level": 2, "cases": cases, "batch": True}, env)
+    assert got == [_want(_data(c), 2) for c in cases]
+
+
+def test_emulated_operator_interface(emu):
+    """orz_lzenc_new/encode/forward (chunk mode, host-driven) through the emulated kernels."""
+    case = {"gen": "text_like", "n": 25000, "seed": 54}
+    got = _run(emu, {"level": 2, "cases": [case], "operators": True})
+    assert got == [_want(_data(case), 2)]
+
+
+def test_emulated_parse_v4_under_random_interleavings(emu):
+    case = {"gen": "text_like", "n": 20000, "seed": 53}
+    got = _run(emu, {"level": 1, "cases": [case]}, {"ORZ_B200_PARSE": "4", "SIMT_SEED": "7"})
+    assert got == [_want(_data(case), 1)]
+
+
+@pytest.fixture(scope="module")
+def scale_model():
+    """Emulator AND oracle rebuilt with 128 KiB blocks / 3000-item chunks: block slides, `forward`, stale tails and
+    chunk cuts (lib.rs:72-86, lz.rs:82-87,128-131) within 150 KB of input."""
+    subprocess.check_call(["make", "-C", SIMT, "liborz_b200_emu_small.so", "orz_oracle_small"], stdout=subprocess.DEVNULL)
+    cli = os.path.join(SIMT, "emu_cli_small")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", cli, os.path.join(SIMT, "emu_cli.cpp"), "-L" + SIMT,
+                           "-lorz_b200_emu_small", "-Wl,-rpath," + SIMT])
+    return cli, os.path.join(SIMT, "orz_oracle_small")
+
+
+@pytest.mark.parametrize("parse,gen,level,seed", [("3", "text_like", 2, None), ("4", "text_like", 2, None),
+                                                  ("4", "low_entropy", 1, "5"), ("3", "low_entropy", 0, "6")])
+def test_scale_model_multi_block_streams(scale_model, tmp_path, parse, gen, level, seed):
+    cli, oracle = scale_model
+    data = getattr(datagen, gen)(150_000, seed=61)
+    src, want, got = tmp_path / "in", tmp_path / "want.orz", tmp_path / "got.orz"
+    src.write_bytes(data)
+    subprocess.check_call([oracle, "encode", str(level), str(src), str(want)], stderr=subprocess.DEVNULL)
+    env = dict(os.environ, ORZ_B200_PARSE=parse, SIMT_SWITCH_LIMIT="60000000000")
+    if seed:
+        env["SIMT_SEED"] = seed
+    subprocess.run([cli, str(level), str(src), str(got)], env=env, check=True, timeout=900, stderr=subprocess.DEVNULL)
+    assert got.read_bytes() == want.read_bytes()
+    back = tmp_path / "back"
+    subprocess.check_call([oracle, "decode", str(want), str(back)], stderr=subprocess.DEVNULL)
+    assert back.read_bytes() == data
 
 
 def test_loader_refuses_the_emulator_build(emu):
