@@ -689,6 +689,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
 
 } // namespace orz
 #include "parse_v4.cuh"
+#include "parse_v5.cuh"
 namespace orz {
 
 // LZEncoder::forward (lz.rs:82-87) in two grid-stride phases.
@@ -1325,12 +1326,43 @@ static void launch_parse4_variant(EncStream *d_streams, int n, cudaStream_t st) 
     ORZ_LAUNCH(kern, n, NW * 32, sizeof(Sh), st, d_streams);
 }
 
+template <int NW, int K, bool PARK, bool STATS>
+static void launch_parse5_variant(EncStream *d_streams, int n, cudaStream_t st) {
+    constexpr int SL = K > 1 ? 2 : 4; // look-ahead = builders * SL positions
+    typedef ParseShared5<Parse5Dims<NW, SL, K, PARK>::NB, SL> Sh;
+    static bool attr_set = false;
+    auto kern = orz_parse5_kernel<NW, SL, K, PARK, STATS>;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sh));
+        attr_set = true;
+    }
+    if (K > 1) ORZ_LAUNCH_CLUSTER(kern, n * K, NW * 32, sizeof(Sh), st, K, d_streams);
+    else ORZ_LAUNCH(kern, n, NW * 32, sizeof(Sh), st, d_streams);
+}
+template <bool STATS>
+static void launch_parse5(EncStream *d_streams, int n, cudaStream_t st) {
+    const char *e;
+    const int k = (e = getenv("ORZ_B200_PARSE_CLUSTER")) ? atoi(e) : 1;
+    const bool park = (e = getenv("ORZ_B200_PARSE_PARK")) ? atoi(e) != 0 : true;
+    const int nw = (e = getenv("ORZ_B200_PARSE_WARPS")) ? atoi(e) : 32;
+    if (k == 8) park ? launch_parse5_variant<32, 8, true, STATS>(d_streams, n, st) : launch_parse5_variant<32, 8, false, STATS>(d_streams, n, st);
+    else if (k == 4) park ? launch_parse5_variant<32, 4, true, STATS>(d_streams, n, st) : launch_parse5_variant<32, 4, false, STATS>(d_streams, n, st);
+    else if (k == 2) park ? launch_parse5_variant<32, 2, true, STATS>(d_streams, n, st) : launch_parse5_variant<32, 2, false, STATS>(d_streams, n, st);
+    else if (nw == 16) park ? launch_parse5_variant<16, 1, true, STATS>(d_streams, n, st) : launch_parse5_variant<16, 1, false, STATS>(d_streams, n, st);
+    else park ? launch_parse5_variant<32, 1, true, STATS>(d_streams, n, st) : launch_parse5_variant<32, 1, false, STATS>(d_streams, n, st);
+}
+
 void launch_parse(EncStream *d_streams, int n, cudaStream_t st) {
     // One stream: v4 (parse_v4.cuh: windowed warp resolver + lock-free builders; measured on a B200, enwik8 -l2:
     // 5.56 MB/s with 16 warps, 4.59 with 32, v3 4.18).  Several streams: v3, whose many-stream behaviour is the
     // measured one.  ORZ_B200_PARSE=3|4 forces a version, ORZ_B200_PARSE_WARPS=8|16|32 the v4 block size.
     const char *ver = getenv("ORZ_B200_PARSE");
     const int pv = ver ? atoi(ver) : (n == 1 ? 4 : 3);
+    if (pv == 5) { // parse_v5.cuh: v4 + cluster builders (ORZ_B200_PARSE_CLUSTER=1|2|4|8), parked warps (ORZ_B200_PARSE_PARK), sleeping idle builders
+        if (getenv("ORZ_B200_STATS")) launch_parse5<true>(d_streams, n, st);
+        else launch_parse5<false>(d_streams, n, st);
+        return;
+    }
     if (pv == 4) {
         const char *w = getenv("ORZ_B200_PARSE_WARPS");
         const int nw = w ? atoi(w) : 16;

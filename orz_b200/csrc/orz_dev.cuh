@@ -12,12 +12,31 @@
 // library is always built by nvcc without this macro.
 #include "simt_rt.h"
 #define ORZ_LAUNCH(kern, grid, block, smem, st, ...) simt::launch(dim3(grid), dim3(block), (smem), [=]() { kern(__VA_ARGS__); })
+#define ORZ_LAUNCH_CLUSTER(kern, grid, block, smem, st, k, ...) \
+    simt::launch(dim3(grid), dim3(block), (smem), [=]() { kern(__VA_ARGS__); }, (k))
 #define ORZ_COST(c) simt::cost(c)   // virtual-clock annotation at a dependent load (latency model, SIMT_VT=1)
 #define ORZ_POLL() simt::poll()     // a spin-loop iteration: let the other fibres run
 #else
 #include <cuda_runtime.h>
 #define ORZ_DYN_SHARED(name) extern __shared__ __align__(16) uint8_t name[]
 #define ORZ_LAUNCH(kern, grid, block, smem, st, ...) kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__)
+// thread-block cluster of k CTAs along x (grid must be a multiple of k)
+#define ORZ_LAUNCH_CLUSTER(kern, grid, block, smem, st, k, ...)                                                     \
+    do {                                                                                                            \
+        cudaLaunchConfig_t cfg_ = {};                                                                               \
+        cfg_.gridDim = dim3(grid);                                                                                  \
+        cfg_.blockDim = dim3(block);                                                                                \
+        cfg_.dynamicSmemBytes = (smem);                                                                             \
+        cfg_.stream = (st);                                                                                         \
+        cudaLaunchAttribute at_[1];                                                                                 \
+        at_[0].id = cudaLaunchAttributeClusterDimension;                                                            \
+        at_[0].val.clusterDim.x = (k);                                                                              \
+        at_[0].val.clusterDim.y = 1;                                                                                \
+        at_[0].val.clusterDim.z = 1;                                                                                \
+        cfg_.attrs = at_;                                                                                           \
+        cfg_.numAttrs = 1;                                                                                          \
+        cudaLaunchKernelEx(&cfg_, kern, __VA_ARGS__);                                                               \
+    } while (0)
 #define ORZ_COST(c) ((void)0)
 #define ORZ_POLL() ((void)0)
 #endif

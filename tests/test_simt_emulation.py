@@ -97,6 +97,18 @@ def test_emulated_parse_v4_matches_oracle(emu, parse):
     assert got == [_want(_data(c), 2) for c in cases]
 
 
+@pytest.mark.parametrize("cluster,park,seed", [("1", "1", None), ("2", "1", None), ("4", "0", "3")])
+def test_emulated_parse_v5_cluster_builders(emu, cluster, park, seed):
+    """parse_v5.cuh: v4 with thread-block-cluster builders publishing over DSMEM, parked warps, sleeping idle builders
+    (the emulator runs the CTAs of a cluster together and maps CTA 0's shared memory for the others)."""
+    env = {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": cluster, "ORZ_B200_PARSE_PARK": park}
+    if seed:
+        env["SIMT_SEED"] = seed
+    cases = [{"gen": "text_like", "n": 12000, "seed": 71}, {"gen": "low_entropy", "n": 12000, "seed": 72}]
+    got = _run(emu, {"level": 2, "cases": cases, "batch": True}, env)
+    assert got == [_want(_data(c), 2) for c in cases]
+
+
 def test_emulated_operator_interface(emu):
     """orz_lzenc_new/encode/forward (chunk mode, host-driven) through the emulated kernels."""
     case = {"gen": "text_like", "n": 25000, "seed": 54}
