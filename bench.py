@@ -108,6 +108,39 @@ def oracle_encode_threads(data_list, level):
     return time.perf_counter() - t0, outs
 
 
+VARIANTS = [
+    {"ORZ_B200_PARSE": "3"},
+    {"ORZ_B200_PARSE": "4", "ORZ_B200_PARSE_WARPS": "16"},
+    {"ORZ_B200_PARSE": "4", "ORZ_B200_PARSE_WARPS": "32"},
+    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "1", "ORZ_B200_PARSE_PARK": "1", "ORZ_B200_PARSE_WARPS": "32"},
+    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "1", "ORZ_B200_PARSE_PARK": "0", "ORZ_B200_PARSE_WARPS": "32"},
+    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "1", "ORZ_B200_PARSE_PARK": "1", "ORZ_B200_PARSE_WARPS": "16"},
+    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "2", "ORZ_B200_PARSE_PARK": "1"},
+    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "4", "ORZ_B200_PARSE_PARK": "1"},
+    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "8", "ORZ_B200_PARSE_PARK": "1"},
+]
+
+
+def probe_variants(nbytes=4_000_000, timeout=90):
+    """Side measurement, NOT the metric: every stage A variant in the tree (v3, v4, the opt-in v5 family) on the first
+    4 MB of the corpus, one subprocess each so that an experimental kernel that faults or hangs cannot lose the bench
+    line.  The headline above is measured on the default path over the whole corpus."""
+    res = []
+    for env in VARIANTS:
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "variant_probe.py"), str(nbytes)] +
+                               [f"{k}={v}" for k, v in env.items()], capture_output=True, text=True, timeout=timeout)
+            line = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else ""
+            res.append(json.loads(line) if p.returncode == 0 and line.startswith("{") else
+                       {"env": env, "error": (p.stderr.strip().splitlines() or ["rc %d" % p.returncode])[-1][:200]})
+        except subprocess.TimeoutExpired:
+            res.append({"env": env, "error": "timeout"})
+        except Exception as e:  # noqa: BLE001
+            res.append({"env": env, "error": repr(e)[:200]})
+    return {"note": "side measurement on the first 4 MB of the corpus, one stream, -l2, parse kernel time (CUDA events); "
+                    "not the metric", "results": res}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -370,6 +403,8 @@ def main():
         out["cpu_baseline"] = {"value": int(np.asarray(sample).size) / best / 1e6, "unit": "MB/s", "cores": 1, "kind": "port",
                                "sample": f"the whole {int(np.asarray(sample).size):,} B corpus as one stream, best of 2, C oracle "
                                          f"(port of the reference; Rust cannot be built here); host has {os.cpu_count()} cores"}
+    if n_gpus == 1 and args.workload == "exact" and not decode_dir and not os.environ.get("ORZ_BENCH_NO_VARIANTS"):
+        out["stage_a_variants"] = probe_variants()
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

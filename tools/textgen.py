@@ -46,6 +46,10 @@ def corpus(n: int):
     """(data, description): real enwik8 (tiled if n > 100 MB) when data/enwik8.xz travelled with the repo, else Markov text."""
     p = os.path.join(ROOT, "data", "enwik8.xz")
     if os.path.exists(p):
+        if n <= 100_000_000:  # a prefix: do not decompress the rest
+            d = np.frombuffer(lzma.open(p).read(n), dtype=np.uint8)
+            if d.size == n:
+                return d.copy(), "enwik8 (data/enwik8.xz)"
         d = np.frombuffer(lzma.open(p).read(), dtype=np.uint8)
         if n <= d.size:
             return d[:n].copy(), "enwik8 (data/enwik8.xz)"

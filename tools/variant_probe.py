@@ -1,0 +1,47 @@
+"""Times ONE stage A variant on a slice of the bench corpus and checks its stream against the default path's.
+
+Run by bench.py in a subprocess per variant (so that a faulting or hanging experimental kernel cannot take the bench
+down): `python tools/variant_probe.py NBYTES KEY=VALUE ...` where the KEY=VALUE pairs are the ORZ_B200_PARSE* switches
+of the variant.  Prints one JSON line {"env", "parse_ms", "mb_s", "identical_to_default"}.  No oracle involved: the
+default path's bit-identity with the oracle is what bench.py itself establishes.
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+KEYS = ("ORZ_B200_PARSE", "ORZ_B200_PARSE_WARPS", "ORZ_B200_PARSE_CLUSTER", "ORZ_B200_PARSE_PARK", "ORZ_B200_PARSE_BUILDERS")
+
+
+def run(data, env):
+    from orz_b200 import Batch
+    for k in KEYS:
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    b = Batch(Batch.ENCODE, [len(data)], cfg=2)
+    b.upload(0, data)
+    b.run()
+    out = b.download(0)
+    ms, _ = b.timing(0)
+    b.close()
+    return out, ms
+
+
+def main():
+    n = int(sys.argv[1])
+    env = dict(a.split("=", 1) for a in sys.argv[2:])
+    assert all(k in KEYS for k in env), env
+    from tools import textgen
+    data, _ = textgen.corpus(n)
+    data = data.tobytes()
+    want, _ = run(data, {})
+    run(data, env)  # warm-up (module load, attribute set)
+    got, ms = run(data, env)
+    print(json.dumps({"env": env, "bytes": n, "parse_ms": round(ms, 2), "mb_s": round(n / ms / 1e3, 3) if ms else None,
+                      "identical_to_default": got == want}))
+
+
+if __name__ == "__main__":
+    main()
