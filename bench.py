@@ -118,11 +118,16 @@ VARIANTS = [
     {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "2", "ORZ_B200_PARSE_PARK": "1"},
     {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "4", "ORZ_B200_PARSE_PARK": "1"},
     {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "8", "ORZ_B200_PARSE_PARK": "1"},
+    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "32"},
+    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "16"},
+    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "16", "ORZ_B200_PARSE_WARPS": "32"},
+    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_CLUSTER": "4"},
+    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_CLUSTER": "8"},
 ]
 
 
 def probe_variants(nbytes=4_000_000, timeout=90):
-    """Side measurement, NOT the metric: every stage A variant in the tree (v3, v4, the opt-in v5 family) on the first
+    """Side measurement, NOT the metric: every stage A variant in the tree (v3, v4, the opt-in v5 / v6 families) on the first
     4 MB of the corpus, one subprocess each so that an experimental kernel that faults or hangs cannot lose the bench
     line.  The headline above is measured on the default path over the whole corpus."""
     res = []

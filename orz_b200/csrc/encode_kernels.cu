@@ -690,6 +690,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
 } // namespace orz
 #include "parse_v4.cuh"
 #include "parse_v5.cuh"
+#include "parse_v6.cuh"
 namespace orz {
 
 // LZEncoder::forward (lz.rs:82-87) in two grid-stride phases.
@@ -1352,12 +1353,45 @@ static void launch_parse5(EncStream *d_streams, int n, cudaStream_t st) {
     else park ? launch_parse5_variant<32, 1, true, STATS>(d_streams, n, st) : launch_parse5_variant<32, 1, false, STATS>(d_streams, n, st);
 }
 
+template <int NW, int K, int G, bool STATS>
+static void launch_parse6_variant(EncStream *d_streams, int n, cudaStream_t st) {
+    constexpr int SL = 2;
+    typedef ParseShared5<Parse6Dims<NW, SL, K, true, G>::NB, SL> Sh;
+    static bool attr_set = false;
+    auto kern = orz_parse6_kernel<NW, SL, K, true, G, STATS>;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sh));
+        attr_set = true;
+    }
+    if (K > 1) ORZ_LAUNCH_CLUSTER(kern, n * K, NW * 32, sizeof(Sh), st, K, d_streams);
+    else ORZ_LAUNCH(kern, n, NW * 32, sizeof(Sh), st, d_streams);
+}
+template <int G, bool STATS>
+static void launch_parse6(EncStream *d_streams, int n, cudaStream_t st) {
+    const char *e;
+    const int k = (e = getenv("ORZ_B200_PARSE_CLUSTER")) ? atoi(e) : 1;
+    const int nw = (e = getenv("ORZ_B200_PARSE_WARPS")) ? atoi(e) : 32;
+    if (k == 8) launch_parse6_variant<32, 8, G, STATS>(d_streams, n, st);
+    else if (k == 4) launch_parse6_variant<32, 4, G, STATS>(d_streams, n, st);
+    else if (k == 2) launch_parse6_variant<32, 2, G, STATS>(d_streams, n, st);
+    else if (nw == 16) launch_parse6_variant<16, 1, G, STATS>(d_streams, n, st);
+    else launch_parse6_variant<32, 1, G, STATS>(d_streams, n, st);
+}
+
 void launch_parse(EncStream *d_streams, int n, cudaStream_t st) {
     // One stream: v4 (parse_v4.cuh: windowed warp resolver + lock-free builders; measured on a B200, enwik8 -l2:
     // 5.56 MB/s with 16 warps, 4.59 with 32, v3 4.18).  Several streams: v3, whose many-stream behaviour is the
     // measured one.  ORZ_B200_PARSE=3|4 forces a version, ORZ_B200_PARSE_WARPS=8|16|32 the v4 block size.
     const char *ver = getenv("ORZ_B200_PARSE");
     const int pv = ver ? atoi(ver) : (n == 1 ? 4 : 3);
+    if (pv == 6) { // parse_v6.cuh: v5 (parked warps) with G-lane builder groups, ORZ_B200_PARSE_GROUP=8|16
+        const char *ge = getenv("ORZ_B200_PARSE_GROUP");
+        const int g = ge ? atoi(ge) : 8;
+        const bool st6 = getenv("ORZ_B200_STATS") != nullptr;
+        if (g == 16) st6 ? launch_parse6<16, true>(d_streams, n, st) : launch_parse6<16, false>(d_streams, n, st);
+        else st6 ? launch_parse6<8, true>(d_streams, n, st) : launch_parse6<8, false>(d_streams, n, st);
+        return;
+    }
     if (pv == 5) { // parse_v5.cuh: v4 + cluster builders (ORZ_B200_PARSE_CLUSTER=1|2|4|8), parked warps (ORZ_B200_PARSE_PARK), sleeping idle builders
         if (getenv("ORZ_B200_STATS")) launch_parse5<true>(d_streams, n, st);
         else launch_parse5<false>(d_streams, n, st);

@@ -44,6 +44,7 @@ simt_switch:
 namespace simt {
 
 Ctx *cur = nullptr;
+int cur_site = 0;
 
 namespace {
 
@@ -67,7 +68,7 @@ struct Fiber {
 
 struct WarpState {
     uint32_t arrived = 0, mask = 0, exist = 0;
-    int op = 0;
+    int op = 0, site = 0;
     uint32_t val[32], param[32];
     Fiber *lanes[32];
 };
@@ -271,9 +272,16 @@ uint32_t collective(int op, uint32_t mask, uint32_t v, uint32_t param) {
     Fiber *f = g_cur;
     WarpState *w = f->w;
     const unsigned lane = f->ctx.lane;
+    const int site = cur_site;
+    cur_site = 0;
     if (w->arrived == 0) {
         w->mask = mask;
         w->op = op;
+        w->site = site;
+    } else if (w->site != site) {
+        fail("SIMT emulator: lanes of one warp reached a collective at different source sites (divergent branch around a "
+             "__shfl/__ballot/__syncwarp: undefined behaviour on the GPU)");
+        switch_to(&g_main);
     } else if (w->mask != mask || w->op != op) {
         fail("SIMT emulator: lanes of one warp are in different collectives (divergent __shfl/__ballot masks)");
         switch_to(&g_main);

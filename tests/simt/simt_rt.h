@@ -56,6 +56,7 @@ extern Ctx *cur;
 
 enum Op { OP_SYNC, OP_IDX, OP_BALLOT, OP_MATCH_ANY, OP_MAX, OP_MIN, OP_ADD, OP_OR, OP_AND };
 uint32_t collective(int op, uint32_t mask, uint32_t v, uint32_t param);
+extern int cur_site;                // source site of the collective being executed (see the macros at the end of this file)
 void syncthreads();
 void cluster_sync();
 void poll();                        // a poll point: lets other fibres run
@@ -318,3 +319,18 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr);
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 template <class F>
 static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+
+// ---- call-site check --------------------------------------------------------------------------------------------
+// On the GPU every lane named in the mask must execute THE SAME warp-collective instruction; two lanes that reach
+// `__shfl_sync` at different places of a divergent branch is undefined behaviour (in practice a hang).  The fibre model
+// would happily pair them up, so every textual use of a collective gets a site number (__COUNTER__) and the runtime
+// fails the launch if the lanes of one collective disagree about it.
+#define __shfl_sync(...) (simt::cur_site = __COUNTER__ + 1, __shfl_sync(__VA_ARGS__))
+#define __shfl_up_sync(...) (simt::cur_site = __COUNTER__ + 1, __shfl_up_sync(__VA_ARGS__))
+#define __shfl_down_sync(...) (simt::cur_site = __COUNTER__ + 1, __shfl_down_sync(__VA_ARGS__))
+#define __shfl_xor_sync(...) (simt::cur_site = __COUNTER__ + 1, __shfl_xor_sync(__VA_ARGS__))
+#define __ballot_sync(...) (simt::cur_site = __COUNTER__ + 1, __ballot_sync(__VA_ARGS__))
+#define __any_sync(...) (simt::cur_site = __COUNTER__ + 1, __any_sync(__VA_ARGS__))
+#define __all_sync(...) (simt::cur_site = __COUNTER__ + 1, __all_sync(__VA_ARGS__))
+#define __match_any_sync(...) (simt::cur_site = __COUNTER__ + 1, __match_any_sync(__VA_ARGS__))
+#define __syncwarp(...) (simt::cur_site = __COUNTER__ + 1, __syncwarp(__VA_ARGS__))

@@ -109,6 +109,45 @@ def test_emulated_parse_v5_cluster_builders(emu, cluster, park, seed):
     assert got == [_want(_data(c), 2) for c in cases]
 
 
+@pytest.mark.parametrize("group,cluster,warps,seed", [("8", "1", "16", None), ("16", "1", "32", "4"), ("8", "2", "32", None)])
+def test_emulated_parse_v6_sub_warp_builders(emu, group, cluster, warps, seed):
+    """parse_v6.cuh: builder warps split into groups of 8 / 16 lanes, one probe per group (segment-wise chain walks,
+    full-mask width-G collectives); the emulator also checks that no collective sits under a group-dependent branch."""
+    env = {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": group, "ORZ_B200_PARSE_CLUSTER": cluster, "ORZ_B200_PARSE_WARPS": warps}
+    if seed:
+        env["SIMT_SEED"] = seed
+    cases = [{"gen": "text_like", "n": 20000, "seed": 81}, {"gen": "low_entropy", "n": 20000, "seed": 82}]
+    for level in (0, 2):
+        got = _run(emu, {"level": level, "cases": cases, "batch": True}, env)
+        assert got == [_want(_data(c), level) for c in cases]
+
+
+def test_emulator_flags_divergent_collectives(tmp_path):
+    """The runtime fails a launch in which lanes of one warp meet in a collective from different source sites."""
+    src = tmp_path / "div.cpp"
+    src.write_text('''
+#include "simt_rt.h"
+#include <cstdio>
+static void kern(unsigned *out) {
+    unsigned v = threadIdx.x;
+    if (threadIdx.x & 1) v = __shfl_sync(0xffffffffu, v, 0);   // odd lanes here ...
+    else v = __shfl_sync(0xffffffffu, v, 1);                    // ... even lanes there: undefined on the GPU
+    out[threadIdx.x] = v;
+}
+int main() {
+    unsigned out[32];
+    simt::launch(dim3(1), dim3(32), 0, [&]() { kern(out); });
+    const char *e = simt::last_error();
+    printf("%s\\n", e ? e : "no error");
+    return e ? 0 : 1;
+}
+''')
+    exe = tmp_path / "div"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", SIMT, "-o", str(exe), str(src), os.path.join(SIMT, "simt_rt.cpp")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "different source sites" in out.stdout
+
+
 def test_emulated_operator_interface(emu):
     """orz_lzenc_new/encode/forward (chunk mode, host-driven) through the emulated kernels."""
     case = {"gen": "text_like", "n": 25000, "seed": 54}
@@ -134,7 +173,8 @@ def scale_model():
 
 
 @pytest.mark.parametrize("parse,gen,level,seed", [("3", "text_like", 2, None), ("4", "text_like", 2, None),
-                                                  ("4", "low_entropy", 1, "5"), ("3", "low_entropy", 0, "6")])
+                                                  ("4", "low_entropy", 1, "5"), ("3", "low_entropy", 0, "6"),
+                                                  ("6", "text_like", 1, "8")])
 def test_scale_model_multi_block_streams(scale_model, tmp_path, parse, gen, level, seed):
     cli, oracle = scale_model
     data = getattr(datagen, gen)(150_000, seed=61)

@@ -12,7 +12,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-KEYS = ("ORZ_B200_PARSE", "ORZ_B200_PARSE_WARPS", "ORZ_B200_PARSE_CLUSTER", "ORZ_B200_PARSE_PARK", "ORZ_B200_PARSE_BUILDERS")
+KEYS = ("ORZ_B200_PARSE", "ORZ_B200_PARSE_WARPS", "ORZ_B200_PARSE_CLUSTER", "ORZ_B200_PARSE_PARK", "ORZ_B200_PARSE_BUILDERS",
+        "ORZ_B200_PARSE_GROUP")
 
 
 def run(data, env):
