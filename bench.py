@@ -126,24 +126,37 @@ VARIANTS = [
 ]
 
 
-def probe_variants(nbytes=4_000_000, timeout=90):
+MULTI_VARIANTS = [  # many independent streams (the segment-parallel extension): (bytes per stream, streams, switches)
+    (1 << 20, 48, {"ORZ_B200_PARSE": "3"}),
+    (1 << 20, 48, {"ORZ_B200_PARSE": "4", "ORZ_B200_PARSE_WARPS": "16"}),
+    (1 << 20, 48, {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "16"}),
+    (1 << 18, 192, {"ORZ_B200_PARSE": "3"}),
+    (1 << 18, 192, {"ORZ_B200_PARSE": "4", "ORZ_B200_PARSE_WARPS": "8"}),
+    (1 << 18, 192, {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "8"}),
+]
+
+
+def probe_variants(nbytes=4_000_000, timeout=90, multi=True):
     """Side measurement, NOT the metric: every stage A variant in the tree (v3, v4, the opt-in v5 / v6 families) on the first
-    4 MB of the corpus, one subprocess each so that an experimental kernel that faults or hangs cannot lose the bench
-    line.  The headline above is measured on the default path over the whole corpus."""
+    4 MB of the corpus as one stream, and a few of them on batches of independent streams, one subprocess each so that an
+    experimental kernel that faults or hangs cannot lose the bench line.  The headline above is measured on the default
+    path over the whole corpus."""
     res = []
-    for env in VARIANTS:
+    jobs = [(nbytes, 1, env) for env in VARIANTS] + (MULTI_VARIANTS if multi else [])
+    for nb, ns, env in jobs:
         try:
-            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "variant_probe.py"), str(nbytes)] +
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "variant_probe.py"), str(nb), str(ns)] +
                                [f"{k}={v}" for k, v in env.items()], capture_output=True, text=True, timeout=timeout)
             line = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else ""
             res.append(json.loads(line) if p.returncode == 0 and line.startswith("{") else
-                       {"env": env, "error": (p.stderr.strip().splitlines() or ["rc %d" % p.returncode])[-1][:200]})
+                       {"env": env, "streams": ns, "error": (p.stderr.strip().splitlines() or ["rc %d" % p.returncode])[-1][:200]})
         except subprocess.TimeoutExpired:
-            res.append({"env": env, "error": "timeout"})
+            res.append({"env": env, "streams": ns, "error": "timeout"})
         except Exception as e:  # noqa: BLE001
-            res.append({"env": env, "error": repr(e)[:200]})
-    return {"note": "side measurement on the first 4 MB of the corpus, one stream, -l2, parse kernel time (CUDA events); "
-                    "not the metric", "results": res}
+            res.append({"env": env, "streams": ns, "error": repr(e)[:200]})
+    return {"note": "side measurement, -l2, stage A kernel time (CUDA events): one stream = the first 4 MB of the corpus; "
+                    "batches = consecutive slices; identical_to_default compares with the default path's streams; not the metric",
+            "results": res}
 
 
 def main():

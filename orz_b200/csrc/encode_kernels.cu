@@ -1375,6 +1375,7 @@ static void launch_parse6(EncStream *d_streams, int n, cudaStream_t st) {
     else if (k == 4) launch_parse6_variant<32, 4, G, STATS>(d_streams, n, st);
     else if (k == 2) launch_parse6_variant<32, 2, G, STATS>(d_streams, n, st);
     else if (nw == 16) launch_parse6_variant<16, 1, G, STATS>(d_streams, n, st);
+    else if (nw == 8) launch_parse6_variant<8, 1, G, STATS>(d_streams, n, st);
     else launch_parse6_variant<32, 1, G, STATS>(d_streams, n, st);
 }
 

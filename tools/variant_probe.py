@@ -1,8 +1,9 @@
 """Times ONE stage A variant on a slice of the bench corpus and checks its stream against the default path's.
 
 Run by bench.py in a subprocess per variant (so that a faulting or hanging experimental kernel cannot take the bench
-down): `python tools/variant_probe.py NBYTES KEY=VALUE ...` where the KEY=VALUE pairs are the ORZ_B200_PARSE* switches
-of the variant.  Prints one JSON line {"env", "parse_ms", "mb_s", "identical_to_default"}.  No oracle involved: the
+down): `python tools/variant_probe.py NBYTES NSTREAMS KEY=VALUE ...` — NSTREAMS independent streams of NBYTES each
+(consecutive slices of the corpus); the KEY=VALUE pairs are the ORZ_B200_PARSE* switches of the variant.  Prints one
+JSON line {"env", "streams", "parse_ms", "mb_s", "identical_to_default"}.  No oracle involved: the
 default path's bit-identity with the oracle is what bench.py itself establishes.
 """
 import json
@@ -16,32 +17,33 @@ KEYS = ("ORZ_B200_PARSE", "ORZ_B200_PARSE_WARPS", "ORZ_B200_PARSE_CLUSTER", "ORZ
         "ORZ_B200_PARSE_GROUP")
 
 
-def run(data, env):
+def run(segs, env):
     from orz_b200 import Batch
     for k in KEYS:
         os.environ.pop(k, None)
     os.environ.update(env)
-    b = Batch(Batch.ENCODE, [len(data)], cfg=2)
-    b.upload(0, data)
+    b = Batch(Batch.ENCODE, [len(s) for s in segs], cfg=2)
+    for i, s in enumerate(segs):
+        b.upload(i, s)
     b.run()
-    out = b.download(0)
+    outs = [b.download(i) for i in range(len(segs))]
     ms, _ = b.timing(0)
     b.close()
-    return out, ms
+    return outs, ms
 
 
 def main():
-    n = int(sys.argv[1])
-    env = dict(a.split("=", 1) for a in sys.argv[2:])
+    n, ns = int(sys.argv[1]), int(sys.argv[2])
+    env = dict(a.split("=", 1) for a in sys.argv[3:])
     assert all(k in KEYS for k in env), env
     from tools import textgen
-    data, _ = textgen.corpus(n)
-    data = data.tobytes()
-    want, _ = run(data, {})
-    run(data, env)  # warm-up (module load, attribute set)
-    got, ms = run(data, env)
-    print(json.dumps({"env": env, "bytes": n, "parse_ms": round(ms, 2), "mb_s": round(n / ms / 1e3, 3) if ms else None,
-                      "identical_to_default": got == want}))
+    data, _ = textgen.corpus(n * ns)
+    segs = [data[i * n:(i + 1) * n].tobytes() for i in range(ns)]
+    want, _ = run(segs, {})
+    run(segs, env)  # warm-up (module load, attribute set)
+    got, ms = run(segs, env)
+    print(json.dumps({"env": env, "bytes": n, "streams": ns, "parse_ms": round(ms, 2),
+                      "mb_s": round(n * ns / ms / 1e3, 3) if ms else None, "identical_to_default": got == want}))
 
 
 if __name__ == "__main__":
