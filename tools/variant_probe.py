@@ -1,10 +1,11 @@
-"""Times ONE stage A variant on a slice of the bench corpus and checks its stream against the default path's.
+"""Times ONE stage A variant on a slice of the bench corpus and checks its streams against stage A v3's.
 
 Run by bench.py in a subprocess per variant (so that a faulting or hanging experimental kernel cannot take the bench
 down): `python tools/variant_probe.py NBYTES NSTREAMS KEY=VALUE ...` — NSTREAMS independent streams of NBYTES each
 (consecutive slices of the corpus); the KEY=VALUE pairs are the ORZ_B200_PARSE* switches of the variant.  Prints one
-JSON line {"env", "streams", "parse_ms", "mb_s", "identical_to_default"}.  No oracle involved: the
-default path's bit-identity with the oracle is what bench.py itself establishes.
+JSON line {"env", "streams", "parse_ms", "mb_s", "identical_to_v3"}: v3 (ORZ_B200_PARSE=3) is the kernel whose
+streams were compared with the oracle's over the whole corpus and in every GPU test of round 1.  No oracle involved:
+bench.py itself compares the stream of the kernel it ends up timing with the oracle's.
 """
 import json
 import os
@@ -22,7 +23,7 @@ def run(segs, env):
     for k in KEYS:
         os.environ.pop(k, None)
     os.environ.update(env)
-    b = Batch(Batch.ENCODE, [len(s) for s in segs], cfg=2)
+    b = Batch(Batch.ENCODE, [len(s) for s in segs], cfg=2, device=int(os.environ.get("ORZ_PROBE_DEVICE", "0")))
     for i, s in enumerate(segs):
         b.upload(i, s)
     b.run()
@@ -39,11 +40,11 @@ def main():
     from tools import textgen
     data, _ = textgen.corpus(n * ns)
     segs = [data[i * n:(i + 1) * n].tobytes() for i in range(ns)]
-    want, _ = run(segs, {})
+    want, _ = run(segs, {"ORZ_B200_PARSE": "3"})
     run(segs, env)  # warm-up (module load, attribute set)
     got, ms = run(segs, env)
     print(json.dumps({"env": env, "bytes": n, "streams": ns, "parse_ms": round(ms, 2),
-                      "mb_s": round(n * ns / ms / 1e3, 3) if ms else None, "identical_to_default": got == want}))
+                      "mb_s": round(n * ns / ms / 1e3, 3) if ms else None, "identical_to_v3": got == want}))
 
 
 if __name__ == "__main__":
