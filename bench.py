@@ -168,8 +168,8 @@ def probe_variants(nbytes=6_000_000, timeout=120, multi=True, done=None):
 
 
 def autotune_stage_a(nbytes=6_000_000, confirm_bytes=18_000_000, timeout=120, device=0):
-    """Pick the stage A kernel for the one-stream workload on THIS GPU.  Every single-CTA variant (clusters are only
-    measured, see probe_variants) encodes the first 6 MB of the corpus (two chunks) in its own process; those whose stream
+    """Pick the stage A kernel for the one-stream workload on THIS GPU.  Every variant of VARIANTS encodes the first 6 MB
+    of the corpus (two chunks) in its own process; those whose stream
     equals stage A v3's are candidates; the fastest wins if it beats the library default by more than 5 %; the winner
     must then reproduce v3's stream on the first 18 MB (a block slide and `forward`).  Returns (switches, results);
     switches == {} keeps the library default.  bench.py compares the whole-corpus stream of whatever it times with the
@@ -178,8 +178,6 @@ def autotune_stage_a(nbytes=6_000_000, confirm_bytes=18_000_000, timeout=120, de
     base = None
     best_env, best = {}, 0.0
     for env in VARIANTS:
-        if int(env.get("ORZ_B200_PARSE_CLUSTER", "1")) > 1:
-            continue
         r = _probe(nbytes, 1, env, timeout, device)
         results.append(r)
         v = r.get("mb_s") if r.get("identical_to_v3") else None
@@ -187,6 +185,8 @@ def autotune_stage_a(nbytes=6_000_000, confirm_bytes=18_000_000, timeout=120, de
             continue
         if env == DEFAULT_VARIANT:
             base = v
+        if int(env.get("ORZ_B200_PARSE_CLUSTER", "1")) > 1:
+            v /= 1.10  # a thread-block cluster (K SMs for one stream) must win by 10 % more than a single-CTA kernel
         if v > best:
             best_env, best = env, v
     if not best_env or (base is not None and best <= base * 1.05):
@@ -375,60 +375,74 @@ def main():
             os.environ.pop(k, None)
         tuned, tune_state = {}, "default kept: " + why
 
-    dev_ms, parse_ms, emit_ms, parse_launches, launches = [], [], [], [], []
-    wall = []
-    e2e_s = []
-    sampler = None
-    for it in range(args.warmup + args.steps):
-        flush.fill_(it & 0xFF)
-        if it == args.warmup:
-            barrier()
-            sampler = ClockSampler(dev) if rank == 0 else None
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        if tuned and it == 0:
-            # first pass with the tuned kernel: it must complete and reproduce the oracle's stream, else back to the default
-            try:
-                batch.run()
-                if tune_check is None:
-                    from oracle import pyoracle
-                    pyoracle.build()
-                    tune_check = pyoracle.encode(streams[0], LEVEL)
-                if batch.download(0) != tune_check:
-                    drop_tuning("the tuned kernel's stream differed from the oracle's")
+    def measure():
+        """W warm-up + K timed passes (resident and end-to-end); returns the per-step lists and the clock sample."""
+        nonlocal tune_check
+        dev_ms, parse_ms, emit_ms, parse_launches, launches = [], [], [], [], []
+        wall = []
+        e2e_s = []
+        sampler = None
+        for it in range(args.warmup + args.steps):
+            flush.fill_(it & 0xFF)
+            if it == args.warmup:
+                barrier()
+                sampler = ClockSampler(dev) if rank == 0 else None
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if tuned and it == 0:
+                # first pass with the tuned kernel: it must complete and reproduce the oracle's stream, else back to the default
+                try:
                     batch.run()
-            except Exception as e:  # noqa: BLE001
-                drop_tuning("the tuned kernel failed: " + repr(e)[:80])
+                    if tune_check is None:
+                        from oracle import pyoracle
+                        pyoracle.build()
+                        tune_check = pyoracle.encode(streams[0], LEVEL)
+                    if batch.download(0) != tune_check:
+                        drop_tuning("the tuned kernel's stream differed from the oracle's")
+                        batch.run()
+                except Exception as e:  # noqa: BLE001
+                    drop_tuning("the tuned kernel failed: " + repr(e)[:80])
+                    batch.run()
+            else:
                 batch.run()
-        else:
-            batch.run()
-        gather_spans()
-        t1 = time.perf_counter()
-        if it >= args.warmup:
-            wall.append(t1 - t0)
-            dev_ms.append(batch.timing(4)[0])
-            pm, pk = batch.timing(3 if decode_dir else 0)
-            em, ek = (0.0, 0) if decode_dir else batch.timing(1)
-            bm, bk = (0.0, 0) if decode_dir else batch.timing(2)
-            parse_ms.append(pm)
-            emit_ms.append(em)
-            parse_launches.append(pk)
-            launches.append(pk + ek + bk)
-        # e2e through the public C ABI with host buffers (one warm-up pass, then every timed step)
-        if it < args.warmup - 1:
-            continue
-        flush.fill_((it + 1) & 0xFF)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        if decode_dir:
-            check(L.orz_decode_batch(dev, n, inp, inl, outp, outc, outl), "orz_decode_batch")
-        else:
-            check(L.orz_encode_batch(dev, C.byref(cfg), n, inp, inl, outp, outc, outl), "orz_encode_batch")
-        t1 = time.perf_counter()
-        if it >= args.warmup:
-            e2e_s.append(t1 - t0)
-    barrier()
-    clocks = sampler.stop() if sampler else None
+            gather_spans()
+            t1 = time.perf_counter()
+            if it >= args.warmup:
+                wall.append(t1 - t0)
+                dev_ms.append(batch.timing(4)[0])
+                pm, pk = batch.timing(3 if decode_dir else 0)
+                em, ek = (0.0, 0) if decode_dir else batch.timing(1)
+                bm, bk = (0.0, 0) if decode_dir else batch.timing(2)
+                parse_ms.append(pm)
+                emit_ms.append(em)
+                parse_launches.append(pk)
+                launches.append(pk + ek + bk)
+            # e2e through the public C ABI with host buffers (one warm-up pass, then every timed step)
+            if it < args.warmup - 1:
+                continue
+            flush.fill_((it + 1) & 0xFF)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if decode_dir:
+                check(L.orz_decode_batch(dev, n, inp, inl, outp, outc, outl), "orz_decode_batch")
+            else:
+                check(L.orz_encode_batch(dev, C.byref(cfg), n, inp, inl, outp, outc, outl), "orz_encode_batch")
+            t1 = time.perf_counter()
+            if it >= args.warmup:
+                e2e_s.append(t1 - t0)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        return dev_ms, parse_ms, emit_ms, parse_launches, launches, wall, e2e_s, clocks
+
+    dev_ms, parse_ms, emit_ms, parse_launches, launches, wall, e2e_s, clocks = measure()
+    if tuned and tune_check is not None:
+        # the tuned kernel was checked on its first pass; its LAST (timed) pass must be the oracle's stream too, and both paths
+        # (resident and host-buffer) must agree — otherwise the measurement is repeated with the library default
+        host = pin_out[0].a if hasattr(pin_out[0], "a") else pin_out[0].numpy()  # (.a: the torch stand-in of the CPU flow test)
+        if batch.download(0) != tune_check or host[: int(outl[0])].tobytes() != tune_check:
+            drop_tuning("a later pass of the tuned kernel differed from the oracle's stream; re-measured")
+            dev_ms, parse_ms, emit_ms, parse_launches, launches, wall, e2e_s, clocks = measure()
+
 
     comp_bytes = sum(batch.result_len(i) for i in range(n))
     # cross-check e2e output against the resident run
