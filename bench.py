@@ -121,6 +121,7 @@ VARIANTS = [
     {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "32"},
     {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "16"},
     {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "16", "ORZ_B200_PARSE_WARPS": "32"},
+    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "4", "ORZ_B200_PARSE_WARPS": "16"},
     {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_CLUSTER": "4"},
     {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_CLUSTER": "8"},
 ]
@@ -133,6 +134,7 @@ MULTI_VARIANTS = [  # many independent streams (the segment-parallel extension):
     (1 << 18, 192, {"ORZ_B200_PARSE": "3"}),
     (1 << 18, 192, {"ORZ_B200_PARSE": "4", "ORZ_B200_PARSE_WARPS": "8"}),
     (1 << 18, 192, {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "8"}),
+    (1 << 18, 192, {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "4", "ORZ_B200_PARSE_WARPS": "8"}),
 ]
 
 

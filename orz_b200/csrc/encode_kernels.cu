@@ -1385,11 +1385,12 @@ void launch_parse(EncStream *d_streams, int n, cudaStream_t st) {
     // measured one.  ORZ_B200_PARSE=3|4 forces a version, ORZ_B200_PARSE_WARPS=8|16|32 the v4 block size.
     const char *ver = getenv("ORZ_B200_PARSE");
     const int pv = ver ? atoi(ver) : (n == 1 ? 4 : 3);
-    if (pv == 6) { // parse_v6.cuh: v5 (parked warps) with G-lane builder groups, ORZ_B200_PARSE_GROUP=8|16
+    if (pv == 6) { // parse_v6.cuh: v5 (parked warps) with G-lane builder groups, ORZ_B200_PARSE_GROUP=4|8|16
         const char *ge = getenv("ORZ_B200_PARSE_GROUP");
         const int g = ge ? atoi(ge) : 8;
         const bool st6 = getenv("ORZ_B200_STATS") != nullptr;
         if (g == 16) st6 ? launch_parse6<16, true>(d_streams, n, st) : launch_parse6<16, false>(d_streams, n, st);
+        else if (g == 4) st6 ? launch_parse6<4, true>(d_streams, n, st) : launch_parse6<4, false>(d_streams, n, st);
         else st6 ? launch_parse6<8, true>(d_streams, n, st) : launch_parse6<8, false>(d_streams, n, st);
         return;
     }
