@@ -342,11 +342,16 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
             uint32_t cur = 0, n_new = 0;
 
             // ---- walk the step chain through the window (lz.rs:131-236); every value below is lane-local
+            // (the loop is the serial chain of the stream: no division, no packing beyond one word, all four broadcasts issued together)
+            const uint32_t head0m = head0 % kRing;
+            const bool need_lazy = fm_len > 0 && fm_len < (uint32_t)(kMatchMax / 2);     // lz.rs:151
+            const uint32_t ce = c | e << 8;
             for (;;) {
                 const bool lwm = cur2 == lwe;                                           // lz.rs:133
-                const uint32_t head = (head0 + pend) % kRing;                            // ring head when this lane's step runs
-                const uint32_t ro = (head + kRing - fm_idx) % kRing;                     // matcher.rs:185
-                const bool need_lazy = fm_len > 0 && fm_len < (uint32_t)(kMatchMax / 2); // lz.rs:151
+                uint32_t head = head0m + pend;                                           // ring head when this lane's step runs (pend <= 32)
+                head = head >= (uint32_t)kRing ? head - kRing : head;
+                uint32_t ro = head + kRing - fm_idx;                                     // matcher.rs:185
+                ro = ro >= (uint32_t)kRing ? ro - kRing : ro;
                 const uint32_t ll1 = fm_len + 1 + (ro < 510u ? 1u : 0u);                 // robitlen < 8  <=>  ro + 2 < 512
                 const uint32_t ll2 = ll1 - (lwm ? 1u : 0u);
                 int lazy_id = 0;
@@ -362,15 +367,14 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
                 const uint32_t adv = emit_match ? fm_len : (word ? 2u : 1u);
                 const uint32_t kind = emit_match ? 2u : (word ? 1u : 0u);
                 // the broadcast of this lane's step, should it be the next one
-                const uint32_t dec = (usable ? 1u : 0u) | kind << 1 | adv << 3 | c << 11 | e << 19; // adv <= 240: 8 bits, e: 13 bits
+                const uint32_t dec = (usable ? 1u : 0u) | kind << 1 | adv << 3;
                 const uint32_t wu = word ? 0xffffffffu : (emit_match ? b.w : b.z);
-                const uint32_t d_s = __shfl_sync(kFull, dec, cur);
-                if (!(d_s & 1u)) break;                                                  // probe (or lazy probe) missing / stale
-                const uint32_t wu_s = __shfl_sync(kFull, wu, cur);
                 // A match step may bump the lenmin of its matched node (matcher.rs:66-71; decided with fm_pl at commit).
                 // Until it is committed, every later probe that matched the same node counts as stale.
-                const uint32_t bump_s = __shfl_sync(kFull, emit_match ? fm_idx : kNoBump, cur);
-                const uint32_t c_s = (d_s >> 11) & 0xffu, e_s = d_s >> 19, kind_s = (d_s >> 1) & 3u, adv_s = (d_s >> 3) & 0xffu;
+                const uint32_t d_s = __shfl_sync(kFull, dec, cur), ce_s = __shfl_sync(kFull, ce, cur);
+                const uint32_t wu_s = __shfl_sync(kFull, wu, cur), bump_s = __shfl_sync(kFull, emit_match ? fm_idx : kNoBump, cur);
+                if (!(d_s & 1u)) break;                                                  // probe (or lazy probe) missing / stale
+                const uint32_t c_s = ce_s & 0xffu, e_s = ce_s >> 8, kind_s = (d_s >> 1) & 3u, adv_s = d_s >> 3;
                 if ((uint32_t)lane == cur) {
                     my_kind = kind;
                     my_head = head;
@@ -464,18 +468,18 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
                 dst[1] = r1;
                 dst[2] = r2;
                 dst[3] = r3;
-                fence5<CL>();
+                // (no fence between the record and the head: a builder that sees the new head early meets an insert of its
+                // own hash entry that is younger than its nb0, which the validation rejects anyway)
                 heads[c * kHeadsStride + e] = (int16_t)new_head;
                 sh.blog[c][(head0 + (uint32_t)__popc(same_c & lt_mask)) % kBlog5] = e | bump << 16;
                 if (!(same_ctx & lt_mask)) sh.cnt[ctx] = cnt_base + (uint32_t)__popc(same_ctx);
             }
-            fence5<CL>();
+            fence5<CL>(); // THE release: every ring store of this window is visible before the insert counts say so
             __syncwarp();
             if (is_step && !(same_c & lt_mask)) v_bcnt[c] = head0 + (uint32_t)__popc(same_c);
             n_items += n_new;
             spos += cur;
-            fence5<CL>();
-            if (lane == 0) *v_spos = spos;
+            if (lane == 0) *v_spos = spos; // a hint for the builders (and the licence to reuse mailbox slots of passed positions)
             __syncwarp();
         }
         if (lane == 0) {
