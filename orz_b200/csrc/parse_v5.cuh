@@ -497,8 +497,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse5_kernel(EncStream *streams)
             Probe4 &pub = sh.pub[(q % NB) * SL + (q / NB) % SL];
             volatile Probe4 *vpub = &pub;
             if (STATS) nbuild++;
-            if (lane == 0) vpub->q = kNone;
-            fence5<CL>();
+            if (lane == 0) vpub->q = kNone; // (ordered before the probe's fields by the fence that follows the bcnt read)
             const uint32_t prev4 = ld_u32_unaligned(win, q - 4); // bytes q-4 .. q-1
             const uint32_t cur4 = ld_u32_unaligned(win, q);      // bytes q .. q+3
             ORZ_COST(120); // window bytes (L1) + hashing

@@ -528,8 +528,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
             Probe4 &pub = sh.pub[(qq % NB) * SL + (qq / NB) % SL];
             volatile Probe4 *vpub = &pub;
             if (STATS && act && sl == 0) nbuild++;
-            if (act && sl == 0) vpub->q = kNone;
-            fence5<CL>();
+            if (act && sl == 0) vpub->q = kNone; // (ordered before the probe's fields by the fence that follows the bcnt read)
             const uint32_t prev4 = ld_u32_unaligned(win, qq - 4); // bytes q-4 .. q-1
             const uint32_t cur4 = ld_u32_unaligned(win, qq);      // bytes q .. q+3
             ORZ_COST(120);
