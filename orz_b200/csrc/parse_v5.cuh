@@ -23,6 +23,10 @@
 namespace orz {
 
 constexpr int kBlog5 = 16; // inserts remembered per bucket (the look-ahead of a cluster is deeper than v4's)
+// Builders do not run further ahead of the parse than this many positions (~40 steps): a probe must be ready one build
+// latency before its turn, and every step it waits beyond that is a chance to go stale (3.5 % within 32 steps, 5.4 %
+// within 64; the per-bucket log holds 16 inserts).  With more builders than that needs, the surplus sleeps.
+constexpr uint32_t kLookahead5 = 192;
 
 #ifdef ORZ_SIMT_EMU
 template <class T>
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse5_kernel(EncStream *streams)
 #pragma unroll
             for (int t = 0; t < SL; t++) {
                 const uint32_t qt = q1 + (uint32_t)t * NB;
-                if (q != kNone || qt >= sbuf_len) continue;
+                if (q != kNone || qt >= sbuf_len || qt >= sp + kLookahead5) continue;
                 const uint32_t have = bcast0(ld_vol_u32(&sh.pub[(qt % NB) * SL + (qt / NB) % SL].q));
                 if (have == kNone || (have & kPosMask) != qt) q = qt;
             }

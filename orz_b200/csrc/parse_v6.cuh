@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
                 const uint32_t qt = q1 + (uint32_t)t * NB;
                 const uint32_t qs = qt < sbuf_len ? qt : q1; // keep the address in range; the result is ignored then
                 const uint32_t have = gshfl<G>(ld_vol_u32(&sh.pub[(qs % NB) * SL + (qs / NB) % SL].q), 0);
-                if (q == kNone && qt < sbuf_len && (have == kNone || (have & kPosMask) != qt)) q = qt;
+                if (q == kNone && qt < sbuf_len && qt < sp + kLookahead5 && (have == kNone || (have & kPosMask) != qt)) q = qt;
             }
             bool act = q != kNone;
             if (!__any_sync(kFull, act)) { // nothing to build in this warp: leave the issue slots to the others

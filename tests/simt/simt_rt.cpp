@@ -382,6 +382,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
     const unsigned nthreads = block.x * block.y * block.z;
     const unsigned nblocks = grid.x * grid.y * grid.z;
     g_switches = 0;
+    g_vt_end = 0;
     if (cluster == 0) cluster = 1;
     if (nthreads == 0 || nblocks == 0) return;
     g_body = &body;
