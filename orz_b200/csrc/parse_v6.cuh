@@ -334,7 +334,6 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
             const uint32_t md1 = mx1 & 0xffu, md2 = (mx2 >> 8) & 0xffu;
             const uint32_t h2 = b.y & 0x7fffu, cur2 = b.y >> 16;
             uint32_t lwe = sh.words[h2];                  // lz.rs:132 (kept current below while the window advances)
-            uint32_t pend = 0;                            // inserts into c decided in this window before this lane's turn
             bool conf0 = !ok, conf1 = !ok1, conf2 = !ok2;
             // what this lane decided when its turn came
             uint32_t my_kind = 0, my_head = 0, my_al = 0, my_lwe = 0;
@@ -343,27 +342,32 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
 
             // ---- walk the step chain through the window (lz.rs:131-236); every value below is lane-local
             // (the loop is the serial chain of the stream: no division, no packing beyond one word, all four broadcasts issued together)
-            const uint32_t head0m = head0 % kRing;
+            // Everything that does not change while the window advances is folded into flags here, so that a lane's decision
+            // is a handful of selects on (rlt, lwm, conf*): lazy thresholds are fm_len+1+rlt and that minus lwm (lz.rs:151-153).
             const bool need_lazy = fm_len > 0 && fm_len < (uint32_t)(kMatchMax / 2);     // lz.rs:151
+            const bool t1a = md1 >= fm_len + 1, t1b = md1 >= fm_len + 2;
+            const bool u0 = md2 >= fm_len, u1 = md2 >= fm_len + 1, u2 = md2 >= fm_len + 2;
+            const bool can_word = p + 1 < sbuf_len;
             const uint32_t ce = c | e << 8;
-            for (;;) {
-                const bool lwm = cur2 == lwe;                                           // lz.rs:133
-                uint32_t head = head0m + pend;                                           // ring head when this lane's step runs (pend <= 32)
-                head = head >= (uint32_t)kRing ? head - kRing : head;
+            uint32_t head = head0 % kRing;                                               // ring head when this lane's step runs
+            bool rlt;                                                                    // robitlen < 8  <=>  reduced offset + 2 < 512
+            {
                 uint32_t ro = head + kRing - fm_idx;                                     // matcher.rs:185
                 ro = ro >= (uint32_t)kRing ? ro - kRing : ro;
-                const uint32_t ll1 = fm_len + 1 + (ro < 510u ? 1u : 0u);                 // robitlen < 8  <=>  ro + 2 < 512
-                const uint32_t ll2 = ll1 - (lwm ? 1u : 0u);
+                rlt = ro < 510u;
+            }
+            for (;;) {
+                const bool lwm = cur2 == lwe;                                           // lz.rs:133
                 int lazy_id = 0;
                 bool usable = !conf0;
                 if (need_lazy) {
                     if (conf1) usable = false;
-                    else if (md1 >= ll1) lazy_id = 1;
+                    else if (rlt ? t1b : t1a) lazy_id = 1;
                     else if (conf2) usable = false;
-                    else if (md2 >= ll2) lazy_id = 2;
+                    else if (rlt == lwm ? u1 : (rlt ? u2 : u0)) lazy_id = 2;
                 }
                 const bool emit_match = fm_len > 0 && lazy_id == 0;
-                const bool word = !emit_match && p + 1 < sbuf_len && lazy_id != 1 && lwm;   // lz.rs:218
+                const bool word = !emit_match && can_word && lazy_id != 1 && lwm;           // lz.rs:218
                 const uint32_t adv = emit_match ? fm_len : (word ? 2u : 1u);
                 const uint32_t kind = emit_match ? 2u : (word ? 1u : 0u);
                 // the broadcast of this lane's step, should it be the next one
@@ -389,7 +393,10 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
                     if (e == e_s || (fm_len > 0 && fm_idx == bump_s)) conf0 = true;
                     if (room0 == 0) conf0 = true;
                     else room0--;
-                    pend++;
+                    head = head + 1 == (uint32_t)kRing ? 0u : head + 1;                  // one more insert ahead of this lane's turn
+                    uint32_t ro = head + kRing - fm_idx;
+                    ro = ro >= (uint32_t)kRing ? ro - kRing : ro;
+                    rlt = ro < 510u;
                 }
                 if (c1 == c_s) {
                     if (e1 == e_s || room1 == 0) conf1 = true;
