@@ -153,10 +153,12 @@ def test_decoder_survives_corrupted_streams():
 def test_eight_builder_variant_and_wide_batch(monkeypatch):
     """The many-stream kernel variant (8 builders per block) must be as exact as the 16-builder one."""
     data = datagen.text_like(250_000, seed=61) + datagen.low_entropy(60_000, seed=62)
+    monkeypatch.setenv("ORZ_B200_PARSE", "3")  # one stream defaults to stage A v4; this test is about v3's 8-builder blocks
     monkeypatch.setenv("ORZ_B200_PARSE_BUILDERS", "8")
     for level in (0, 2):
         assert orz_b200.encode(data, level) == pyoracle.encode(data, level)
     monkeypatch.delenv("ORZ_B200_PARSE_BUILDERS")
+    monkeypatch.delenv("ORZ_B200_PARSE")
     segs = [data[i * 997:(i * 997) + 3000 + (i % 7) * 500] for i in range(300)]  # 300 streams: the launcher picks 8 builders
     encs = orz_b200.encode_batch(segs, 1)
     for i in (0, 1, 57, 123, 299):
