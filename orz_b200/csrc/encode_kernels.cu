@@ -1318,6 +1318,7 @@ static void launch_parse_variant(EncStream *d_streams, int n, cudaStream_t st) {
 template <int NW, int SL, bool STATS>
 static void launch_parse4_variant(EncStream *d_streams, int n, cudaStream_t st) {
     typedef ParseShared4<NW - 1, SL> Sh;
+    static_assert(sizeof(Sh) <= 227 * 1024, "stage A v4: shared memory exceeds an SM");
     static bool attr_set = false;
     auto kern = orz_parse4_kernel<NW, SL, STATS>;
     if (!attr_set) {
@@ -1331,6 +1332,7 @@ template <int NW, int K, bool PARK, bool STATS>
 static void launch_parse5_variant(EncStream *d_streams, int n, cudaStream_t st) {
     constexpr int SL = K > 1 ? 2 : 4; // look-ahead = builders * SL positions
     typedef ParseShared5<Parse5Dims<NW, SL, K, PARK>::NB, SL> Sh;
+    static_assert(sizeof(Sh) <= 227 * 1024, "stage A v5: shared memory of CTA 0 exceeds an SM");
     static bool attr_set = false;
     auto kern = orz_parse5_kernel<NW, SL, K, PARK, STATS>;
     if (!attr_set) {
@@ -1355,8 +1357,9 @@ static void launch_parse5(EncStream *d_streams, int n, cudaStream_t st) {
 
 template <int NW, int K, int G, bool STATS>
 static void launch_parse6_variant(EncStream *d_streams, int n, cudaStream_t st) {
-    constexpr int SL = 2;
+    constexpr int SL = K > 1 ? 1 : 2; // mailbox slots per group: a cluster has more groups than the 192-position look-ahead needs
     typedef ParseShared5<Parse6Dims<NW, SL, K, true, G>::NB, SL> Sh;
+    static_assert(sizeof(Sh) <= 227 * 1024, "stage A v6: shared memory of CTA 0 exceeds an SM");
     static bool attr_set = false;
     auto kern = orz_parse6_kernel<NW, SL, K, true, G, STATS>;
     if (!attr_set) {
@@ -1371,8 +1374,8 @@ static void launch_parse6(EncStream *d_streams, int n, cudaStream_t st) {
     const char *e;
     const int k = (e = getenv("ORZ_B200_PARSE_CLUSTER")) ? atoi(e) : 1;
     const int nw = (e = getenv("ORZ_B200_PARSE_WARPS")) ? atoi(e) : 32;
-    if (k == 8) launch_parse6_variant<32, 8, G, STATS>(d_streams, n, st);
-    else if (k == 4) launch_parse6_variant<32, 4, G, STATS>(d_streams, n, st);
+    if (k == 8 && G >= 8) launch_parse6_variant<32, (G >= 8 ? 8 : 4), G, STATS>(d_streams, n, st); // (G = 4: 8 CTAs of 4-lane groups would not fit the mailbox)
+    else if (k >= 4) launch_parse6_variant<32, 4, G, STATS>(d_streams, n, st);
     else if (k == 2) launch_parse6_variant<32, 2, G, STATS>(d_streams, n, st);
     else if (nw == 16) launch_parse6_variant<16, 1, G, STATS>(d_streams, n, st);
     else if (nw == 8) launch_parse6_variant<8, 1, G, STATS>(d_streams, n, st);
