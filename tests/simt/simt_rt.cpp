@@ -385,6 +385,11 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
     g_vt_end = 0;
     if (cluster == 0) cluster = 1;
     if (nthreads == 0 || nblocks == 0) return;
+    // the launch limits of the target (sm_100a): what the GPU would refuse, the emulator refuses too
+    if (nthreads > 1024 || smem > 227 * 1024 || cluster > 8 || nblocks % cluster != 0) {
+        fail("SIMT emulator: launch exceeds the device limits (1024 threads, 227 KiB shared memory, clusters of 8, grid % cluster)");
+        return;
+    }
     g_body = &body;
     for (unsigned b0 = 0; b0 < nblocks; b0 += cluster) {
         Cluster C;
