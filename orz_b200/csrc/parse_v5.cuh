@@ -501,8 +501,33 @@ __global__ void __launch_bounds__(NW * 32) orz_parse5_kernel(EncStream *streams)
                 const uint32_t have = bcast0(ld_vol_u32(&sh.pub[(qt % NB) * SL + (qt / NB) % SL].q));
                 if (have == kNone || (have & kPosMask) != qt) q = qt;
             }
-            if (q == kNone) { // nothing to build: leave the issue slots to the others
-                __nanosleep(128);
+            if (q == kNone) {
+                // Nothing to build.  Before sleeping, look whether one of this builder's published probes went stale (the same
+                // test the resolver makes when the probe enters its window): a probe invalidated by an insert that is still
+                // tens of steps away from it can be rebuilt before the parse arrives, instead of costing it one build latency.
+                bool stale = false;
+#pragma unroll
+                for (int t = 0; t < SL; t++) {
+                    const uint32_t qt = q1 + (uint32_t)t * NB;
+                    if (qt >= sbuf_len || qt >= sp + kLookahead5) continue;
+                    Probe4 &pb = sh.pub[(qt % NB) * SL + (qt / NB) % SL];
+                    volatile Probe4 *vpb = &pb;
+                    const uint32_t w0 = bcast0(ld_vol_u32(&vpb->q));
+                    const uint32_t nb_p = bcast0(ld_vol_u32(&vpb->nb0)), ces = bcast0(ld_vol_u32(&vpb->ces)), fmw = bcast0(ld_vol_u32(&vpb->fm));
+                    const uint32_t pc = ces & 0xffu, pe = (ces >> 8) & 0x1fffu, psafe = ces >> 21;
+                    const uint32_t dnew = bcast0(ld_vol_u32(&v_bcnt[pc])) - nb_p;
+                    bool bad = dnew > (uint32_t)kBlog5 || dnew > psafe;
+                    if (!bad && (uint32_t)lane < dnew) {
+                        const uint32_t ent = ld_vol_u32(&sh.blog[pc][(nb_p + (uint32_t)lane) % kBlog5]);
+                        bad = (ent & 0xffffu) == pe || ((fmw & 0xffu) > 0 && (ent >> 16) == ((fmw >> 8) & 0xfffu));
+                    }
+                    if (__any_sync(kFull, bad && (w0 & kPosMask) == qt && w0 != kNone)) {
+                        if (lane == 0) vpb->q = kNone; // (the resolver's compare-and-swap writes the same value)
+                        stale = true;
+                        if (STATS) nabort += 1ull << 32;
+                    }
+                }
+                if (!stale) __nanosleep(128); // leave the issue slots to the others
                 continue;
             }
             Probe4 &pub = sh.pub[(q % NB) * SL + (q / NB) % SL];

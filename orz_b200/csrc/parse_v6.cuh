@@ -527,8 +527,37 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
                 if (q == kNone && qt < sbuf_len && qt < sp + kLookahead5 && (have == kNone || (have & kPosMask) != qt)) q = qt;
             }
             bool act = q != kNone;
-            if (!__any_sync(kFull, act)) { // nothing to build in this warp: leave the issue slots to the others
-                __nanosleep(128);
+            if (!__any_sync(kFull, act)) {
+                // Nothing to build in this warp.  Before sleeping every group re-checks its published probes with the resolver's
+                // own staleness test (parse_v5.cuh): a probe invalidated by an insert that is still tens of steps away from it
+                // can be rebuilt before the parse arrives.
+                bool stale = false;
+#pragma unroll
+                for (int t = 0; t < SL; t++) {
+                    const uint32_t qt = q1 + (uint32_t)t * NB;
+                    const bool in_range = qt < sbuf_len && qt < sp + kLookahead5;
+                    const uint32_t qs = in_range ? qt : q1 % NB; // (any valid slot address; the result is ignored)
+                    Probe4 &pb = sh.pub[(qs % NB) * SL + (qs / NB) % SL];
+                    volatile Probe4 *vpb = &pb;
+                    const uint32_t w0 = gshfl<G>(ld_vol_u32(&vpb->q), 0);
+                    const uint32_t nb_p = gshfl<G>(ld_vol_u32(&vpb->nb0), 0), ces = gshfl<G>(ld_vol_u32(&vpb->ces), 0);
+                    const uint32_t fmw = gshfl<G>(ld_vol_u32(&vpb->fm), 0);
+                    const bool mine = in_range && w0 != kNone && (w0 & kPosMask) == qt;
+                    const uint32_t pc = ces & 0xffu, pe = (ces >> 8) & 0x1fffu, psafe = ces >> 21;
+                    const uint32_t dnew = gshfl<G>(ld_vol_u32(&v_bcnt[pc]), 0) - nb_p;
+                    bool bad = dnew > (uint32_t)kBlog5 || dnew > psafe;
+                    if (mine && !bad)
+                        for (uint32_t k = (uint32_t)sl; k < dnew; k += G) {
+                            const uint32_t ent = ld_vol_u32(&sh.blog[pc][(nb_p + k) % kBlog5]);
+                            if ((ent & 0xffffu) == pe || ((fmw & 0xffu) > 0 && (ent >> 16) == ((fmw >> 8) & 0xfffu))) bad = true;
+                        }
+                    const bool gbad = gballot<G>(mine && bad, g0) != 0;
+                    if (gbad) {
+                        if (sl == 0) vpb->q = kNone; // (the resolver's compare-and-swap writes the same value)
+                        stale = true;
+                    }
+                }
+                if (!__any_sync(kFull, stale)) __nanosleep(128); // leave the issue slots to the others
                 continue;
             }
             const uint32_t qq = act ? q : sp; // inactive groups run along on a harmless position, publish nothing
