@@ -894,6 +894,9 @@ struct EmitShared {
     uint8_t lens[3][kSymStride];
     uint16_t codes[3][kSymStride];
     uint32_t scan[kEmitThreads];
+    uint32_t stage[kEmitWarps][32];   // stage B: a batch's (symbol | unlikely << 16) for the lane that runs the rank coder
+    uint16_t rank_out[kEmitWarps][32];
+    uint32_t rcp[kSymStride];         // ceil(2^32 / d): exact (esum >> 4) / d by multiply-high
     uint32_t next_ctx;
     uint32_t num_counted;
     uint32_t hdr_bits;
@@ -916,6 +919,7 @@ __global__ void __launch_bounds__(kEmitThreads) orz_emit_kernel(EncStream *strea
     for (int i = tid; i < 256; i += kEmitThreads) sh.hist2[i] = 0;
     for (int i = tid; i < kSymStride; i += kEmitThreads) sh.symcount[i] = 0;
     for (int i = tid; i < kNumCtx; i += kEmitThreads) sh.cnt[i] = S->ctx_count[i];
+    for (int i = tid; i < kSymStride; i += kEmitThreads) sh.rcp[i] = i < 2 ? 0u : (uint32_t)(((1ull << 32) + (unsigned)i - 1) / (unsigned)i);
     if (tid == 0) sh.next_ctx = 0;
     __syncthreads();
 
@@ -1015,51 +1019,53 @@ __global__ void __launch_bounds__(kEmitThreads) orz_emit_kernel(EncStream *strea
                     eml = it.eml;
                 }
                 const int m = cntc - off < 32 ? (int)(cntc - off) : 32;
-                uint32_t myrank = 0;
-                for (int q = 0; q < m; q++) {
-                    const uint32_t v = __shfl_sync(0xffffffffu, sym, q);
-                    const uint32_t vu = __shfl_sync(0xffffffffu, unl, q);
-                    const uint32_t i = tab.index[v];
-                    const uint32_t iun = tab.index[vu];
-                    // update (symrank.rs:61-97); every lane executes the same stores with the same values
-                    if (ecnt > (uint32_t)kNumSym) {
-                        ecnt = ecnt * 9 / 10;
-                        esum = esum * 9 / 10;
+                // The rank update is a serial state machine per context (symrank.rs:38-97), and the largest context of a chunk
+                // (about a tenth of its items) is the critical path of this kernel.  So ONE lane runs it on the shared table
+                // with nothing else on its dependency chain: the batch's symbols are staged in shared memory by all lanes, the
+                // ranks come back the same way, and sum/16/cnt is a multiply-high with a precomputed reciprocal.
+                sh.stage[warp][lane] = sym | unl << 16;
+                __syncwarp();
+                if (lane == 0) {
+                    for (int q = 0; q < m; q++) {
+                        const uint32_t w = sh.stage[warp][q];
+                        const uint32_t v = w & 0xffffu, vu = w >> 16;
+                        const uint32_t i = tab.index[v];
+                        const uint32_t iun = tab.index[vu];
+                        if (ecnt > (uint32_t)kNumSym) { // symrank.rs:61-66
+                            ecnt = ecnt * 9 / 10;
+                            esum = esum * 9 / 10;
+                        }
+                        ecnt += 1;
+                        esum += i;
+                        // (esum >> 4) / ecnt: exact by reciprocal while (esum >> 4) * ecnt < 2^32 (esum starts at 1,000,000 and decays)
+                        const uint32_t a16 = esum >> 4;
+                        const uint32_t quo = (ecnt < 2 || esum >= (1u << 24)) ? a16 / ecnt : __umulhi(a16, sh.rcp[ecnt]);
+                        const uint32_t sub = ((i >> 4) + quo) & 0xffffu; // u16 arithmetic
+                        uint32_t next_i = i > sub ? i - sub : 0;
+                        if (next_i < (i >> 1)) next_i = i >> 1;
+                        const uint32_t d = i - next_i;
+                        if (d == 1) { // symrank.rs:75-97: 2- or 3-way rotation
+                            const uint16_t nv1 = tab.value[next_i];
+                            tab.index[v] = (uint16_t)next_i;
+                            tab.value[i] = nv1;
+                            tab.index[nv1] = (uint16_t)i;
+                            tab.value[next_i] = (uint16_t)v;
+                        } else if (d > 1) {
+                            const uint32_t ni2 = next_i, ni1 = next_i + d / 2;
+                            const uint16_t nv1 = tab.value[ni1];
+                            const uint16_t nv2 = tab.value[ni2];
+                            tab.value[i] = nv1;
+                            tab.index[nv1] = (uint16_t)i;
+                            tab.value[ni1] = nv2;
+                            tab.index[nv2] = (uint16_t)ni1;
+                            tab.value[ni2] = (uint16_t)v;
+                            tab.index[v] = (uint16_t)ni2;
+                        }
+                        sh.rank_out[warp][q] = (uint16_t)((i == iun) ? (uint32_t)(kNumSym - 1) : i - (i > iun)); // symrank.rs:43-46
                     }
-                    ecnt += 1;
-                    esum += i;
-                    const uint32_t sub = ((i >> 4) + ((esum >> 4) / ecnt)) & 0xffffu; // u16 arithmetic
-                    uint32_t next_i = i > sub ? i - sub : 0;
-                    if (next_i < (i >> 1)) next_i = i >> 1;
-                    const uint32_t d = i - next_i;
-                    // Every lane replays the same update on the shared table.  All reads come first, then a warp
-                    // barrier, then the writes: no lane may see the table half-rewritten by a faster lane.
-                    const uint32_t ni2 = next_i, ni1 = next_i + d / 2;
-                    uint16_t nv1 = 0, nv2 = 0;
-                    if (d == 1) {
-                        nv1 = tab.value[next_i];
-                    } else if (d > 1) {
-                        nv1 = tab.value[ni1];
-                        nv2 = tab.value[ni2];
-                    }
-                    __syncwarp();
-                    if (d == 1) {
-                        tab.index[v] = (uint16_t)next_i;
-                        tab.value[i] = nv1;
-                        tab.index[nv1] = (uint16_t)i;
-                        tab.value[next_i] = (uint16_t)v;
-                    } else if (d > 1) {
-                        tab.value[i] = nv1;
-                        tab.index[nv1] = (uint16_t)i;
-                        tab.value[ni1] = nv2;
-                        tab.index[nv2] = (uint16_t)ni1;
-                        tab.value[ni2] = (uint16_t)v;
-                        tab.index[v] = (uint16_t)ni2;
-                    }
-                    const uint32_t r = (i == iun) ? (uint32_t)(kNumSym - 1) : i - (i > iun); // symrank.rs:43-46
-                    if (lane == q) myrank = r;
-                    __syncwarp();
                 }
+                __syncwarp();
+                const uint32_t myrank = sh.rank_out[warp][lane];
                 if (have) {
                     items[k].symbol = (uint16_t)myrank;
                     atomicAdd(&sh.hist1[flags & 1u][myrank], 1u);
