@@ -132,6 +132,7 @@ MULTI_VARIANTS = [  # many independent streams (the segment-parallel extension):
     (1 << 20, 48, {"ORZ_B200_PARSE": "4", "ORZ_B200_PARSE_WARPS": "16"}),
     (1 << 20, 48, {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "16"}),
     (1 << 18, 192, {"ORZ_B200_PARSE": "3"}),
+    (1 << 18, 192, {"ORZ_B200_PARSE": "3", "ORZ_B200_DBG": "64"}),
     (1 << 18, 192, {"ORZ_B200_PARSE": "4", "ORZ_B200_PARSE_WARPS": "8"}),
     (1 << 18, 192, {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "8"}),
     (1 << 18, 192, {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "4", "ORZ_B200_PARSE_WARPS": "8"}),

@@ -579,7 +579,10 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
                     k = kt;
                 }
             }
-            if (q == kNone) continue;
+            if (q == kNone) {
+                if (dbg_flags & 64u) __nanosleep(100); // ORZ_B200_DBG=64: idle builders sleep instead of spinning (to be measured with many streams per SM)
+                continue;
+            }
             ProbePub &pub = sh.pub[q % NS];
             volatile ProbePub *vpub = &pub;
             uint32_t &my_q = pq[k], &my_c = pc[k], &my_ver = pver[k];

@@ -144,7 +144,7 @@ struct EncStream {
     uint32_t items_cap;
     uint32_t depth0, depth1, depth2; // LZCfg (lz.rs:32-37)
     int32_t self_driven;  // 1: stream mode (kernel runs the lib.rs loop), 0: chunk mode (host drives)
-    uint32_t dbg_flags;   // measurement switches (ORZ_B200_DBG): 1 no re-stamp, 8 executor cycle counters, 32 builder counters
+    uint32_t dbg_flags;   // measurement switches (ORZ_B200_DBG): 1 no re-stamp, 8 executor cycle counters, 32 builder counters, 64 v3 idle builders sleep
     // mutable
     uint32_t bhead[kNumBuckets];
     uint32_t ctx_count[kNumCtx];

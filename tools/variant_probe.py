@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 KEYS = ("ORZ_B200_PARSE", "ORZ_B200_PARSE_WARPS", "ORZ_B200_PARSE_CLUSTER", "ORZ_B200_PARSE_PARK", "ORZ_B200_PARSE_BUILDERS",
-        "ORZ_B200_PARSE_GROUP")
+        "ORZ_B200_PARSE_GROUP", "ORZ_B200_DBG")
 
 
 def run(segs, env):
