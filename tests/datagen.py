@@ -43,6 +43,20 @@ def low_entropy(n: int, seed: int = 3) -> bytes:
     return bytes(out[:n])
 
 
+def long_chains(n: int, seed: int = 4) -> bytes:
+    """Three 5-byte strings repeated thousands of times with different continuations: every occurrence lands on the same
+    (context, hash entry) chain, so chain walks run to the depth limit, past the 29 links of a ring-record snapshot
+    (multi-round gathers, snapshot source switches) while the matches themselves stay short."""
+    rng = np.random.default_rng(seed)
+    pats = [b" zqxj", b" kwvb", b"-mmmm"]
+    out = bytearray()
+    while len(out) < n:
+        out += pats[int(rng.integers(0, 3))] + bytes(rng.integers(97, 123, size=int(rng.integers(1, 4)), dtype=np.uint8))
+        if rng.random() < 0.3:
+            out += bytes(rng.integers(32, 127, size=int(rng.integers(1, 12)), dtype=np.uint8))
+    return bytes(out[:n])
+
+
 def enwik8(n: int = None, offset: int = 0):
     """First n bytes of enwik8 if data/enwik8.xz travelled with the repo, else None."""
     p = os.path.join(ROOT, "data", "enwik8.xz")

@@ -18,7 +18,8 @@ from tests import datagen  # noqa: E402
 e8 = datagen.enwik8(6_000_000)
 two_chunks = e8 if e8 is not None else datagen.text_like(6_000_000, seed=91)   # > 2^20 items: a chunk cut (lz.rs:128-131)
 two_blocks = (datagen.text_like(3_000_000, seed=92) + datagen.low_entropy(2_000_000, seed=93)) * 4  # 20 MB: slide + forward
-for name, data, level in (("two chunks", two_chunks, 2), ("two blocks", two_blocks, 1)):
+deep = datagen.long_chains(1_500_000, seed=94)  # chain walks to the depth limit, past one ring-record snapshot
+for name, data, level in (("two chunks", two_chunks, 2), ("two blocks", two_blocks, 1), ("long chains", deep, 2)):
     got = orz_b200.encode(data, level)
     want = pyoracle.encode(data, level)
     if got != want:

@@ -27,7 +27,7 @@ def test_tiny_inputs(data, level):
 
 
 @pytest.mark.parametrize("level", [0, 1, 2])
-@pytest.mark.parametrize("gen,n", [("text_like", 300_000), ("random_bytes", 70_000), ("low_entropy", 400_000)])
+@pytest.mark.parametrize("gen,n", [("text_like", 300_000), ("random_bytes", 70_000), ("low_entropy", 400_000), ("long_chains", 400_000)])
 def test_encode_matches_oracle(gen, n, level):
     data = getattr(datagen, gen)(n)
     want = pyoracle.encode(data, level)

@@ -148,6 +148,17 @@ int main() {
     assert out.returncode == 0 and "different source sites" in out.stdout
 
 
+@pytest.mark.parametrize("env", [{"ORZ_B200_PARSE": "3"}, {"ORZ_B200_PARSE": "4"}, {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "2"},
+                                 {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "16"},
+                                 {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "4", "ORZ_B200_PARSE_WARPS": "16", "SIMT_SEED": "6"}])
+def test_emulated_long_chain_walks(emu, env):
+    """Chains far longer than one gather round / one 29-link snapshot (datagen.long_chains): multi-round walks in v3-v5,
+    segment-wise walks with snapshot source switches in v6."""
+    case = {"gen": "long_chains", "n": 30000, "seed": 4}
+    got = _run(emu, {"level": 2, "cases": [case]}, env)
+    assert got == [_want(_data(case), 2)]
+
+
 def test_emulated_operator_interface(emu):
     """orz_lzenc_new/encode/forward (chunk mode, host-driven) through the emulated kernels."""
     case = {"gen": "text_like", "n": 25000, "seed": 54}
