@@ -185,7 +185,7 @@ def scale_model():
 
 @pytest.mark.parametrize("parse,gen,level,seed", [("3", "text_like", 2, None), ("4", "text_like", 2, None),
                                                   ("4", "low_entropy", 1, "5"), ("3", "low_entropy", 0, "6"),
-                                                  ("6", "text_like", 1, "8")])
+                                                  ("6", "text_like", 1, "8"), ("6", "long_chains", 2, None)])
 def test_scale_model_multi_block_streams(scale_model, tmp_path, parse, gen, level, seed):
     cli, oracle = scale_model
     data = getattr(datagen, gen)(150_000, seed=61)
