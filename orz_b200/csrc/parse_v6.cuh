@@ -454,7 +454,12 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
                     it.eml = (uint8_t)((aux >> 8) & 0xffu);
                     it.flags = (uint8_t)(my_al | 2u);
                     mlen = fm_len;
-                    if (node_lenmin(fm_pl) <= fm_len && fm_idx != new_head) {            // matcher.rs:66-71
+                    // matcher.rs:66-71.  The reference bumps the matched node and THEN writes its new node; a bump whose target
+                    // is overwritten by this step or by a later step of this window (slots my_head+1 .. my_head+n_after of the
+                    // bucket) is dead, and issuing it from this lane would race with that lane's record store.
+                    const uint32_t n_after = (uint32_t)__popc(same_c & ~lt_mask);        // steps of this window in bucket c from this one on
+                    const uint32_t ahead = (fm_idx + kRing - my_head) % kRing;
+                    if (node_lenmin(fm_pl) <= fm_len && !(ahead >= 1 && ahead <= n_after)) {
                         const uint32_t lm = fm_len + 1 < 127u ? fm_len + 1 : 127u;
                         nodes[c * kNodesStride + fm_idx].pl = node_pos(fm_pl) | lm << 25;
                         bump = fm_idx;
