@@ -3,6 +3,8 @@
 // Scheduling modes (environment):
 //   default            FIFO: a fibre runs until it blocks in a collective / barrier or reaches a poll point
 //   SIMT_SEED=n        seeded random choice of the next fibre at every poll point and wake-up (race shaking)
+//   SIMT_REVERSE=1     FIFO, but the lanes of a warp leave every collective in DESCENDING lane order: code between two
+//                      collectives that only works because lane 0 (or "the earlier lane") happens to run first fails
 //   SIMT_VT=1          virtual-time order: always run the runnable fibre with the smallest virtual clock; the
 //                      kernels advance the clock with ORZ_COST(cycles) at their dependent loads, so a spin loop
 //                      observes a flag exactly when its writer's clock says it was written.  This turns the
@@ -99,6 +101,7 @@ bool g_error_pending = false;
 // scheduler state
 bool g_vt_mode = false;
 bool g_random = false;
+bool g_reverse = false; // SIMT_REVERSE=1: lanes resume from a collective in descending lane order (exposes code that leans on lane 0 running first)
 uint64_t g_rng = 0x9e3779b97f4a7c15ull;
 unsigned long long g_seq = 0;
 unsigned long long g_switches = 0, g_switch_limit = 0;
@@ -247,6 +250,7 @@ void read_env() {
         g_random = true;
         g_rng ^= (uint64_t)strtoull(e, nullptr, 10) * 0x2545f4914f6cdd1dull + 1;
     }
+    if (const char *e = getenv("SIMT_REVERSE")) g_reverse = atoi(e) != 0;
     if (const char *e = getenv("SIMT_SWITCH_LIMIT")) g_switch_limit = strtoull(e, nullptr, 10);
     if (const char *e = getenv("SIMT_POLL_COST")) g_poll_cost = atoi(e);
     if (const char *e = getenv("SIMT_COLL_COST")) g_coll_cost = atoi(e);
@@ -340,11 +344,12 @@ uint32_t collective(int op, uint32_t mask, uint32_t v, uint32_t param) {
     }
     w->arrived = 0;
     // the other lanes go to the BACK of the queue: a warp that spins on collectives only must not starve the rest
-    for (unsigned l = 0; l < 32; l++) {
+    for (unsigned k = 0; k < 32; k++) {
+        const unsigned l = g_reverse ? 31 - k : k;
         if (!((mask >> l) & 1u) || l == lane) continue;
         push_back(w->lanes[l]);
     }
-    if (g_vt_mode || g_random) { // let the scheduler order this lane with the rest
+    if (g_vt_mode || g_random || g_reverse) { // let the scheduler order this lane with the rest
         push_back(f);
         block_current();
     }
