@@ -104,7 +104,8 @@ def test_emulated_parse_v5_cluster_builders(emu, cluster, park, seed):
     env = {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": cluster, "ORZ_B200_PARSE_PARK": park}
     if seed:
         env["SIMT_SEED"] = seed
-    cases = [{"gen": "text_like", "n": 12000, "seed": 71}, {"gen": "low_entropy", "n": 12000, "seed": 72}]
+    n = 12000 if cluster in ("1", "2") else 5000  # (4 CTAs = 4096 fibres: keep the emulation short)
+    cases = [{"gen": "text_like", "n": n, "seed": 71}, {"gen": "low_entropy", "n": n, "seed": 72}]
     got = _run(emu, {"level": 2, "cases": cases, "batch": True}, env)
     assert got == [_want(_data(c), 2) for c in cases]
 
@@ -188,7 +189,7 @@ def scale_model():
                                                   ("6", "text_like", 1, "8"), ("6", "long_chains", 2, None)])
 def test_scale_model_multi_block_streams(scale_model, tmp_path, parse, gen, level, seed):
     cli, oracle = scale_model
-    data = getattr(datagen, gen)(150_000, seed=61)
+    data = getattr(datagen, gen)(150_000 if seed is None else 100_000, seed=61)  # (random scheduling is the slower mode)
     src, want, got = tmp_path / "in", tmp_path / "want.orz", tmp_path / "got.orz"
     src.write_bytes(data)
     subprocess.check_call([oracle, "encode", str(level), str(src), str(want)], stderr=subprocess.DEVNULL)
