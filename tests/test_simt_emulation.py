@@ -85,7 +85,7 @@ def test_emulated_v3_variants(emu):
     assert got == [_want(_data(case), 2)]
 
 
-@pytest.mark.parametrize("parse", ["4:32", "4:16", "4:8"])
+@pytest.mark.parametrize("parse", ["4:32", "4:8"])
 def test_emulated_parse_v4_matches_oracle(emu, parse):
     """Stage A v4 (windowed warp resolver, lock-free builders; parse_v4.cuh) forced for a batch, 32/16/8-warp blocks."""
     ver, _, warps = parse.partition(":")
@@ -118,9 +118,9 @@ def test_emulated_parse_v6_sub_warp_builders(emu, group, cluster, warps, seed):
     if seed:
         env["SIMT_SEED"] = seed
     cases = [{"gen": "text_like", "n": 20000, "seed": 81}, {"gen": "low_entropy", "n": 20000, "seed": 82}]
-    for level in (0, 2):
-        got = _run(emu, {"level": level, "cases": cases, "batch": True}, env)
-        assert got == [_want(_data(c), level) for c in cases]
+    level = 0 if seed else 2
+    got = _run(emu, {"level": level, "cases": cases, "batch": True}, env)
+    assert got == [_want(_data(c), level) for c in cases]
 
 
 def test_emulator_flags_divergent_collectives(tmp_path):
