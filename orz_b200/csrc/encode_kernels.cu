@@ -1339,7 +1339,10 @@ static void launch_parse4_variant(EncStream *d_streams, int n, cudaStream_t st) 
 
 template <int NW, int K, bool PARK, bool STATS>
 static void launch_parse5_variant(EncStream *d_streams, int n, cudaStream_t st) {
-    constexpr int SL = K > 1 ? 2 : 4; // look-ahead = builders * SL positions
+    // mailbox slots per builder: enough for the 192-position look-ahead cap (kLookahead5) whatever the builder count
+    constexpr int NBv = Parse5Dims<NW, 1, K, PARK>::NB;
+    constexpr int SLw = ((int)kLookahead5 + NBv - 1) / NBv;
+    constexpr int SL = SLw < 1 ? 1 : (SLw > 8 ? 8 : SLw);
     typedef ParseShared5<Parse5Dims<NW, SL, K, PARK>::NB, SL> Sh;
     static_assert(sizeof(Sh) <= 227 * 1024, "stage A v5: shared memory of CTA 0 exceeds an SM");
     static bool attr_set = false;
@@ -1366,7 +1369,10 @@ static void launch_parse5(EncStream *d_streams, int n, cudaStream_t st) {
 
 template <int NW, int K, int G, bool STATS>
 static void launch_parse6_variant(EncStream *d_streams, int n, cudaStream_t st) {
-    constexpr int SL = K > 1 ? 1 : 2; // mailbox slots per group: a cluster has more groups than the 192-position look-ahead needs
+    // mailbox slots per group: enough for the 192-position look-ahead cap (kLookahead5) whatever the group count
+    constexpr int NBv = Parse6Dims<NW, 1, K, true, G>::NB;
+    constexpr int SLw = ((int)kLookahead5 + NBv - 1) / NBv;
+    constexpr int SL = SLw < 1 ? 1 : (SLw > 8 ? 8 : SLw);
     typedef ParseShared5<Parse6Dims<NW, SL, K, true, G>::NB, SL> Sh;
     static_assert(sizeof(Sh) <= 227 * 1024, "stage A v6: shared memory of CTA 0 exceeds an SM");
     static bool attr_set = false;
