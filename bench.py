@@ -115,12 +115,14 @@ VARIANTS = [
     {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "1", "ORZ_B200_PARSE_PARK": "1", "ORZ_B200_PARSE_WARPS": "32"},
     {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "1", "ORZ_B200_PARSE_PARK": "0", "ORZ_B200_PARSE_WARPS": "32"},
     {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "1", "ORZ_B200_PARSE_PARK": "1", "ORZ_B200_PARSE_WARPS": "16"},
+    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "1", "ORZ_B200_PARSE_PARK": "0", "ORZ_B200_PARSE_WARPS": "16"},
     {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "2", "ORZ_B200_PARSE_PARK": "1"},
     {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "4", "ORZ_B200_PARSE_PARK": "1"},
     {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "8", "ORZ_B200_PARSE_PARK": "1"},
     {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "32"},
     {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "16"},
     {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "16", "ORZ_B200_PARSE_WARPS": "32"},
+    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "16", "ORZ_B200_PARSE_WARPS": "16"},
     {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "4", "ORZ_B200_PARSE_WARPS": "16"},
     {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_CLUSTER": "4"},
     {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_CLUSTER": "8"},
