@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
             const uint32_t h2 = b.y & 0x7fffu, cur2 = b.y >> 16;
             uint32_t lwe = sh.words[h2];                  // lz.rs:132 (kept current below while the window advances)
             bool conf0 = !ok, conf1 = !ok1, conf2 = !ok2;
+            bool stale_ce = false; // a step of this window inserted this probe's own hash entry: stale for certain once committed
             // what this lane decided when its turn came
             uint32_t my_kind = 0, my_head = 0, my_al = 0, my_lwe = 0;
             unsigned stepmask = 0;
@@ -391,6 +392,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
                 // keep every lane's inputs current: the insert of step `cur` into bucket c_s, and its words update
                 if (c == c_s) {
                     if (e == e_s || (fm_len > 0 && fm_idx == bump_s)) conf0 = true;
+                    if (e == e_s) stale_ce = true;
                     if (room0 == 0) conf0 = true;
                     else room0--;
                     head = head + 1 == (uint32_t)kRing ? 0u : head + 1;                  // one more insert ahead of this lane's turn
@@ -492,6 +494,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse6_kernel(EncStream *streams)
             n_items += n_new;
             spos += cur;
             if (lane == 0) *v_spos = spos; // a hint for the builders (and the licence to reuse mailbox slots of passed positions)
+            // probes ahead that this window's inserts made stale for certain go back to their builders now, not one window later
+            if (stale_ce && ready && !is_step && p >= spos) atomicCAS(&P->q, a.x, kNone);
             __syncwarp();
         }
         if (lane == 0) {
