@@ -13,10 +13,12 @@
 #include <vector>
 
 namespace orz {
-void launch_parse(EncStream *, int, cudaStream_t);
+void launch_parse(EncStream *, int, bool v7, cudaStream_t);
 void launch_emit(EncStream *, int, cudaStream_t);
 void launch_enc_begin(EncStream *, int, cudaStream_t);
-void launch_enc_forward(EncStream *, uint32_t, cudaStream_t);
+void launch_enc_advance(EncStream *, int, cudaStream_t);
+void launch_enc_forward(EncStream *, uint32_t, bool v7, cudaStream_t);
+bool parse7_stats_enabled();
 void launch_decode(DecStream *, int, cudaStream_t);
 void launch_dec_forward(DecStream *, uint32_t, cudaStream_t);
 } // namespace orz
@@ -33,6 +35,26 @@ using namespace orz;
     } while (0)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Every entry point works on the batch's device and leaves the caller's current device as it found it.
+struct DevGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DevGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DevGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define DEV_GUARD(dev)              \
+    DevGuard dev_guard_(dev);       \
+    if (!dev_guard_.ok) return ORZ_ECUDA
+
+// stage A v7 (parse_v7.cuh) keeps ~0.6 GB of key lists per stream: used for up to this many streams per batch
+static const int kV7MaxStreams = 8;
+static const size_t kV7MaxDepth = 48;
 
 #ifdef ORZ_SIMT_EMU
 // Only the test-tier emulator build (tests/simt/) exports this marker; orz_b200/_lib.py refuses to load a library
@@ -111,6 +133,7 @@ struct orz_batch {
     std::vector<uint64_t> result_len;
     int32_t *h_status_pinned = nullptr;
     bool chunk_mode = false; // operator interface: host drives chunks
+    bool v7 = false;         // encoder state in the v7 layout (key lists), else ring records + hash chains
     KernelTimer timer;
     bool ran = false;
 };
@@ -120,7 +143,7 @@ static int check_device(int device) {
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ORZ_ECUDA;
     cudaDeviceProp p;
     if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return ORZ_ECUDA;
-    if (p.major < 10) return ORZ_ECUDA; // the kernels are built for sm_100a only
+    if (p.major != 10) return ORZ_ECUDA; // the library embeds an sm_100a cubin only
     return ORZ_OK;
 }
 
@@ -171,7 +194,7 @@ struct ArenaPlan {
 
 static void batch_destroy(orz_batch *b) {
     if (!b) return;
-    cudaSetDevice(b->device);
+    DevGuard g(b->device);
     if (b->st) cudaStreamSynchronize(b->st);
     if (b->arena) cudaFree(b->arena);
     if (b->h_status_pinned) cudaFreeHost(b->h_status_pinned);
@@ -188,7 +211,8 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
         return nullptr;
     }
     if ((*err = check_device(device)) != ORZ_OK) return nullptr;
-    if (cudaSetDevice(device) != cudaSuccess) {
+    DevGuard g(device);
+    if (!g.ok) {
         *err = ORZ_ECUDA;
         return nullptr;
     }
@@ -202,6 +226,11 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
     b->n = n;
     b->chunk_mode = chunk_mode;
     if (cfg) b->cfg = *cfg;
+    if (mode == 0) {
+        const bool deep = cfg->match_depth > kV7MaxDepth || cfg->lazy_match_depth1 > kV7MaxDepth || cfg->lazy_match_depth2 > kV7MaxDepth;
+        b->v7 = n <= kV7MaxStreams && (chunk_mode || !deep) && !getenv("ORZ_B200_LEGACY_STAGE_A");
+    }
+    const bool v7 = b->v7;
     b->d_in.resize(n);
     b->d_out.resize(n);
     b->in_cap.resize(n);
@@ -215,7 +244,7 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
 
     ArenaPlan plan;
     struct Offs {
-        size_t in, out, win, nodes, heads, words, symranks, items, sorted, payload, zero_lo, zero_hi;
+        size_t in, out, win, nodes, heads, words, symranks, items, sorted, payload, zero_lo, zero_hi, klist, kcnt, lm, gext;
         size_t win_alloc;
         uint32_t win_lo, win_hi, items_cap, payload_cap;
     };
@@ -243,10 +272,21 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
             o.zero_lo = plan.take(0, 256);
             o.win_alloc = (o.win_lo == 0 ? kSentinel : 0) + (size_t)(o.win_hi - o.win_lo);
             o.win = plan.take(o.win_alloc, 256);
-            o.nodes = plan.take(sizeof(ENode) * kNumBuckets * kNodesStride);
+            o.nodes = o.heads = o.klist = o.kcnt = o.lm = o.gext = 0;
+            if (v7) {
+                o.kcnt = plan.take(sizeof(uint32_t) * kNumBuckets * kHeadsStride);
+                o.lm = plan.take((size_t)kNumBuckets * kNodesStride);
+            } else {
+                o.nodes = plan.take(sizeof(ENode) * kNumBuckets * kNodesStride);
+            }
             o.words = plan.take(65536);
             o.zero_hi = plan.take(0, 256);
-            o.heads = plan.take(sizeof(int16_t) * kNumBuckets * kHeadsStride);
+            if (v7) {
+                o.klist = plan.take(sizeof(uint2) * kNumBuckets * kHeadsStride * 64);
+                o.gext = plan.take(sizeof(uint32_t) * 512 * 48);
+            } else {
+                o.heads = plan.take(sizeof(int16_t) * kNumBuckets * kHeadsStride);
+            }
             o.symranks = plan.take(sizeof(SymRank) * kNumCtx);
             o.items = plan.take(sizeof(Item) * o.items_cap);
             o.sorted = plan.take(sizeof(uint32_t) * o.items_cap);
@@ -290,8 +330,13 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
             S.win = (o.win_lo == 0) ? (A + o.win + kSentinel) : (A + o.win - o.win_lo);
             S.win_lo = o.win_lo;
             S.win_hi = o.win_hi;
-            S.nodes = reinterpret_cast<ENode *>(A + o.nodes);
-            S.heads = reinterpret_cast<int16_t *>(A + o.heads);
+            S.v7 = v7 ? 1u : 0u;
+            S.nodes = v7 ? nullptr : reinterpret_cast<ENode *>(A + o.nodes);
+            S.heads = v7 ? nullptr : reinterpret_cast<int16_t *>(A + o.heads);
+            S.klist = v7 ? reinterpret_cast<uint2 *>(A + o.klist) : nullptr;
+            S.kcnt = v7 ? reinterpret_cast<uint32_t *>(A + o.kcnt) : nullptr;
+            S.lm = v7 ? A + o.lm : nullptr;
+            S.gext = v7 ? reinterpret_cast<uint32_t *>(A + o.gext) : nullptr;
             S.words = reinterpret_cast<uint16_t *>(A + o.words);
             S.symranks = reinterpret_cast<SymRank *>(A + o.symranks);
             S.items = reinterpret_cast<Item *>(A + o.items);
@@ -345,7 +390,7 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
 static int batch_reset_state(orz_batch *b) {
     for (int i = 0; i < b->n; i++) {
         CU_TRY(cudaMemsetAsync(b->zero_lo[i], 0, (size_t)(b->zero_hi[i] - b->zero_lo[i]), b->st));
-        if (b->mode == 0)
+        if (b->mode == 0 && !b->v7)
             CU_TRY(cudaMemsetAsync(b->heads[i], 0xff, sizeof(int16_t) * kNumBuckets * kHeadsStride, b->st));
     }
     if (b->mode == 0) {
@@ -381,7 +426,7 @@ extern "C" void orz_batch_free(orz_batch *b) { batch_destroy(b); }
 
 extern "C" int orz_batch_upload(orz_batch *b, int i, const uint8_t *host, size_t n) {
     if (!b || i < 0 || i >= b->n || n > b->in_cap[i] || (n && !host)) return ORZ_EARG;
-    CU_TRY(cudaSetDevice(b->device));
+    DEV_GUARD(b->device);
     if (n) CU_TRY(cudaMemcpyAsync(b->d_in[i], host, n, cudaMemcpyHostToDevice, b->st));
     CU_TRY(cudaMemsetAsync(b->d_in[i] + n, 0, 64, b->st));
     b->in_len[i] = n;
@@ -390,7 +435,7 @@ extern "C" int orz_batch_upload(orz_batch *b, int i, const uint8_t *host, size_t
 
 extern "C" int orz_batch_run(orz_batch *b) {
     if (!b) return ORZ_EARG;
-    CU_TRY(cudaSetDevice(b->device));
+    DEV_GUARD(b->device);
     b->timer.reset();
     const int whole = b->timer.begin(4, b->st); // class 4: the whole run, reset included
     int rc = batch_reset_state(b);
@@ -404,11 +449,16 @@ extern "C" int orz_batch_run(orz_batch *b) {
             if ((rc = fetch_status(b, &all_done))) return rc;
             if (all_done) break;
             id = b->timer.begin(0, b->st);
-            launch_parse(b->d_enc, b->n, b->st);
+            launch_parse(b->d_enc, b->n, b->v7, b->st);
             b->timer.end(id, b->st);
             id = b->timer.begin(1, b->st);
             launch_emit(b->d_enc, b->n, b->st);
             b->timer.end(id, b->st);
+            if (b->v7) { // end of a block: slide + forward + next block's load, grid-wide (no-ops otherwise)
+                id = b->timer.begin(2, b->st);
+                launch_enc_advance(b->d_enc, b->n, b->st);
+                b->timer.end(id, b->st);
+            }
             CU_TRY(cudaGetLastError());
         }
         // result lengths
@@ -416,7 +466,17 @@ extern "C" int orz_batch_run(orz_batch *b) {
         CU_TRY(cudaMemcpyAsync(tmp.data(), b->d_enc, sizeof(EncStream) * b->n, cudaMemcpyDeviceToHost, b->st));
         CU_TRY(cudaStreamSynchronize(b->st));
         for (int i = 0; i < b->n; i++) b->result_len[i] = tmp[i].out_pos;
-        if (getenv("ORZ_B200_STATS")) {
+        if (b->v7 && parse7_stats_enabled()) {
+            unsigned long long d[8] = {0}, c[8] = {0};
+            for (int i = 0; i < b->n; i++)
+                for (int k = 0; k < 8; k++) d[k] += tmp[i].dbg[k], c[k] += tmp[i].dbg7[k];
+            const double st = d[0] ? (double)d[0] : 1.0;
+            fprintf(stderr,
+                    "orz_b200 stage A v7: steps %llu windows %llu (%.2f steps/window) polls-not-ready %llu repairs %llu (%.4f/step) builds %llu (%.2f/step); "
+                    "resolver cycles/step: total %.1f = load %.1f + walk %.1f + hand-over %.1f + repair %.1f + wait %.1f\n",
+                    d[0], d[1], d[1] ? (double)d[0] / d[1] : 0.0, d[2], d[3], d[3] / st, d[4], d[4] / st, c[0] / st, c[1] / st, c[2] / st, c[3] / st,
+                    c[4] / st, c[5] / st);
+        } else if (getenv("ORZ_B200_STATS")) {
             unsigned long long d[8] = {0};
             for (int i = 0; i < b->n; i++)
                 for (int k = 0; k < 8; k++) d[k] += tmp[i].dbg[k];
@@ -462,7 +522,7 @@ extern "C" int orz_batch_download(orz_batch *b, int i, uint8_t *host, size_t cap
     if (b->status[i] < 0) return b->status[i];
     const size_t n = (size_t)b->result_len[i];
     if (n > cap) return ORZ_ENOSPC;
-    CU_TRY(cudaSetDevice(b->device));
+    DEV_GUARD(b->device);
     if (n) CU_TRY(cudaMemcpyAsync(host, b->d_out[i], n, cudaMemcpyDeviceToHost, b->st));
     CU_TRY(cudaStreamSynchronize(b->st));
     if (len) *len = n;
@@ -497,12 +557,14 @@ struct BatchCache {
     ~BatchCache() {
         if (b) batch_destroy(b);
     }
-} g_cache;
+} g_caches[16]; // one cached batch (and one lock) per device: calls on different GPUs neither serialise nor evict each other
 } // namespace
 
 static int run_host_batch(int device, int mode, const orz_lzcfg *cfg, int n, const uint8_t *const *in, const size_t *in_len,
                           uint8_t *const *out, const size_t *out_cap, size_t *out_len) {
     if (n <= 0 || !in || !in_len || !out || !out_cap || !out_len) return ORZ_EARG;
+    if (device < 0 || device >= 16) return ORZ_ECUDA;
+    BatchCache &g_cache = g_caches[device];
     std::lock_guard<std::mutex> lock(g_cache.mu);
     bool reuse = g_cache.b && g_cache.device == device && g_cache.mode == mode && g_cache.n == n &&
                  (mode != 0 || (cfg->match_depth == g_cache.cfg.match_depth && cfg->lazy_match_depth1 == g_cache.cfg.lazy_match_depth1 &&
@@ -641,6 +703,7 @@ extern "C" int orz_decode_segmented(int device, const uint8_t *in, size_t n, uin
     size_t raw = 0;
     if (!out_len || orz_segmented_raw_len(in, n, &raw) != ORZ_OK) return ORZ_EINVAL;
     const size_t seg_size = get32(in + 16), nseg = get32(in + 20);
+    if (nseg > 0x7fffffffull || nseg > (n - kSegHdr) / kSegEnt) return ORZ_EINVAL; // untrusted count: bounded by the table it must fit in
     const size_t table_end = kSegHdr + nseg * kSegEnt;
     if (table_end > n || (nseg && seg_size == 0) || raw > nseg * (uint64_t)seg_size) return ORZ_EINVAL;
     if (raw > out_cap) return ORZ_ENOSPC;
@@ -711,8 +774,8 @@ extern "C" void orz_lzenc_free(orz_lzenc *e) {
 extern "C" int orz_lzenc_forward(orz_lzenc *e, size_t forward_len) {
     if (!e) return ORZ_EARG;
     orz_batch *b = e->b;
-    CU_TRY(cudaSetDevice(b->device));
-    launch_enc_forward(b->d_enc, (uint32_t)(forward_len > 0x1ffffffu ? 0x1ffffffu : forward_len), b->st);
+    DEV_GUARD(b->device);
+    launch_enc_forward(b->d_enc, (uint32_t)(forward_len > 0x1ffffffu ? 0x1ffffffu : forward_len), b->v7, b->st);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(b->st));
     e->last_sbuf = nullptr; // the caller slid its window (lib.rs:83): force a re-upload
@@ -723,7 +786,7 @@ extern "C" int orz_lzenc_encode(orz_lzenc *e, const orz_lzcfg *cfg, const uint8_
     if (!e || !cfg || !sbuf || !tbuf || !spos_out || !tlen_out) return ORZ_EARG;
     if (sbuf_len > kBlockSize || spos >= sbuf_len || spos < 4) return ORZ_EARG;
     orz_batch *b = e->b;
-    CU_TRY(cudaSetDevice(b->device));
+    DEV_GUARD(b->device);
     EncStream &H = b->enc[0];
     const bool cont = e->started && sbuf == e->last_sbuf && sbuf_len == e->last_len && spos == e->last_spos && spos != kPrematch;
     if (!cont) { // (re)upload the window including both sentinels: those bytes are bit-visible
@@ -739,7 +802,9 @@ extern "C" int orz_lzenc_encode(orz_lzenc *e, const orz_lzcfg *cfg, const uint8_
     CU_TRY(cudaMemcpyAsync(&b->d_enc[0].depth0, &p, sizeof p, cudaMemcpyHostToDevice, b->st));
     uint32_t ss[2] = {(uint32_t)spos, (uint32_t)sbuf_len};
     CU_TRY(cudaMemcpyAsync(&b->d_enc[0].spos, ss, sizeof ss, cudaMemcpyHostToDevice, b->st));
-    launch_parse(b->d_enc, 1, b->st);
+    if (b->v7 && (cfg->match_depth > kV7MaxDepth || cfg->lazy_match_depth1 > kV7MaxDepth || cfg->lazy_match_depth2 > kV7MaxDepth))
+        return ORZ_EARG; // the key-list layout holds 48 candidates per position (main.rs:97-102 uses at most 45); ORZ_B200_LEGACY_STAGE_A=1 lifts this
+    launch_parse(b->d_enc, 1, b->v7, b->st);
     launch_emit(b->d_enc, 1, b->st);
     CU_TRY(cudaGetLastError());
     EncStream R;
@@ -779,7 +844,7 @@ extern "C" void orz_lzdec_free(orz_lzdec *d) {
 extern "C" int orz_lzdec_forward(orz_lzdec *d, size_t forward_len) {
     if (!d) return ORZ_EARG;
     orz_batch *b = d->b;
-    CU_TRY(cudaSetDevice(b->device));
+    DEV_GUARD(b->device);
     if (forward_len == 0) return ORZ_OK;
     if (forward_len > kBlockSize) forward_len = kBlockSize;
     // mirror the caller's copy_within (lib.rs:121) on the device window, then rebase the ring (lz.rs:359-364)
@@ -791,10 +856,11 @@ extern "C" int orz_lzdec_forward(orz_lzdec *d, size_t forward_len) {
         } else { // overlapping ranges: stage through a temporary
             uint8_t *tmp = nullptr;
             CU_TRY(cudaMalloc(&tmp, keep));
-            cudaMemcpyAsync(tmp, win + forward_len, keep, cudaMemcpyDeviceToDevice, b->st);
-            cudaMemcpyAsync(win, tmp, keep, cudaMemcpyDeviceToDevice, b->st);
-            cudaStreamSynchronize(b->st);
+            cudaError_t ce = cudaMemcpyAsync(tmp, win + forward_len, keep, cudaMemcpyDeviceToDevice, b->st);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(win, tmp, keep, cudaMemcpyDeviceToDevice, b->st);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(b->st);
             cudaFree(tmp);
+            CU_TRY(ce);
         }
     }
     launch_dec_forward(b->d_dec, (uint32_t)forward_len, b->st);
@@ -808,7 +874,7 @@ extern "C" int orz_lzdec_decode(orz_lzdec *d, const uint8_t *tbuf, size_t tlen, 
     if (tlen == 0 || tlen >= kTbufLen) return ORZ_EINVAL; // lib.rs:111-113
     if (spos < 4 || spos > kBlockSize || sbuf_cap < kBlockSize) return ORZ_EARG;
     orz_batch *b = d->b;
-    CU_TRY(cudaSetDevice(b->device));
+    DEV_GUARD(b->device);
     CU_TRY(cudaMemcpyAsync(b->d_in[0], tbuf, tlen, cudaMemcpyHostToDevice, b->st));
     CU_TRY(cudaMemsetAsync(b->d_in[0] + tlen, 0, 16, b->st));
     uint64_t il = tlen;

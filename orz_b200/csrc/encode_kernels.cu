@@ -14,6 +14,7 @@
 #include "orz_dev.cuh"
 
 #include <cstdlib>
+#include <cstring>
 
 namespace orz {
 
@@ -692,8 +693,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse_kernel(EncStream *streams) 
 
 } // namespace orz
 #include "parse_v4.cuh"
-#include "parse_v5.cuh"
-#include "parse_v6.cuh"
+#include "parse_v7.cuh"
 namespace orz {
 
 // LZEncoder::forward (lz.rs:82-87) in two grid-stride phases.
@@ -1241,6 +1241,13 @@ __global__ void __launch_bounds__(kEmitThreads) orz_emit_kernel(EncStream *strea
         }
         return;
     }
+    if (S->v7) { // slide, forward and the next block's load run grid-wide in orz_enc_advance_kernel
+        if (tid == 0) {
+            S->out_pos = opos;
+            S->need_slide = 1;
+        }
+        return;
+    }
     // slide: copy_within(len-PREMATCH.., 0) (lib.rs:83); the window is the full 33,554,431-byte slice here
     uint8_t *win = S->win;
     for (uint32_t i = tid; i < (kPrematch + 15) / 16; i += kEmitThreads) {
@@ -1313,148 +1320,166 @@ __global__ void __launch_bounds__(256) orz_enc_forward_kernel(EncStream *streams
 
 size_t emit_smem_bytes() { return sizeof(EmitShared); }
 
-template <int NW, int NB, bool STATS>
-static void launch_parse_variant(EncStream *d_streams, int n, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(orz_parse_kernel<NW, NB, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseShared));
-        attr_set = true;
+// End of a block for v7 streams (lib.rs:83-84,72), grid-wide.  phase 0: slide the window (copy_within(len-PREMATCH.., 0)) and
+// rebase the key lists (LZEncoder::forward, lz.rs:82-87); phase 1: read the next block into [PREMATCH, PREMATCH+rd).
+// The two phases are separate launches because the load overwrites the slide's source.
+__global__ void __launch_bounds__(256) orz_enc_advance_kernel(EncStream *streams, int nstreams, int phase) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    for (int si = 0; si < nstreams; si++) {
+        EncStream *S = &streams[si];
+        if (S->status != 0 || !S->need_slide) continue;
+        uint8_t *win = S->win;
+        if (phase == 0) {
+            for (size_t i = gid; i < (kPrematch + 15) / 16; i += gsz) {
+                // source and destination are 16,777,216 apart and 16 B aligned; ranges do not overlap
+                const uint4 v = *reinterpret_cast<const uint4 *>(win + kBlockNew + 16u * i);
+                if (16u * i + 16u <= kPrematch) {
+                    *reinterpret_cast<uint4 *>(win + 16u * i) = v;
+                } else {
+                    const uint8_t *vb = reinterpret_cast<const uint8_t *>(&v);
+                    for (uint32_t b = 0; 16u * i + b < kPrematch; b++) win[16u * i + b] = vb[b];
+                }
+            }
+            enc7_forward_rebase(S->klist, S->kcnt, kBlockNew, gid, gsz);
+        } else {
+            const uint64_t in_pos = S->in_pos, in_len = S->in_len;
+            const uint64_t rem = in_len - in_pos;
+            const uint32_t rd = rem < kBlockNew ? (uint32_t)rem : kBlockNew;
+            const uint8_t *src = S->in + in_pos;
+            // win + PREMATCH is 1 short of 16-byte alignment: byte head, then 16-byte stores from 16-byte loads when `src` allows
+            const uint32_t headb = rd < 1u ? rd : 1u;
+            if (gid == 0) for (uint32_t i = 0; i < headb; i++) win[kPrematch + i] = src[i];
+            const uint32_t body = (rd - headb) / 16u;
+            if (((uintptr_t)(src + headb) & 15u) == 0) {
+                for (size_t i = gid; i < body; i += gsz)
+                    *reinterpret_cast<uint4 *>(win + kPrematch + headb + 16u * i) = *reinterpret_cast<const uint4 *>(src + headb + 16u * i);
+            } else {
+                for (size_t i = gid; i < (size_t)body * 16u; i += gsz) win[kPrematch + headb + i] = src[headb + i];
+            }
+            for (size_t i = (size_t)headb + (size_t)body * 16u + gid; i < rd; i += gsz) win[kPrematch + i] = src[i];
+        }
     }
-    auto kern = orz_parse_kernel<NW, NB, STATS>;
+}
+// after phase 1 of every stream: the lib.rs:72 loop state of the new block (one thread per stream)
+__global__ void orz_enc_advance_done_kernel(EncStream *streams, int nstreams) {
+    const int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= nstreams) return;
+    EncStream *S = &streams[si];
+    if (S->status != 0 || !S->need_slide) return;
+    const uint64_t in_pos = S->in_pos, rem = S->in_len - in_pos;
+    const uint32_t rd = rem < kBlockNew ? (uint32_t)rem : kBlockNew;
+    S->in_pos = in_pos + rd;
+    S->spos = kPrematch;
+    S->sbuf_len = kPrematch + rd;
+    S->need_slide = 0;
+}
+
+// LZEncoder::forward for the chunk-level API (lz.rs:82-87), v7 layout
+__global__ void __launch_bounds__(256) orz_enc7_forward_kernel(EncStream *streams, uint32_t forward_len) {
+    EncStream *S = &streams[0];
+    enc7_forward_rebase(S->klist, S->kcnt, forward_len, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: set it before every launch (cheap), not once per process
+template <class Kern>
+static void set_smem_attr(Kern kern, size_t bytes) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+template <int NW, int NB>
+static void launch_parse_variant(EncStream *d_streams, int n, cudaStream_t st) {
+    auto kern = orz_parse_kernel<NW, NB, false>;
+    set_smem_attr(kern, sizeof(ParseShared));
     ORZ_LAUNCH(kern, n, NW * 32, sizeof(ParseShared), st, d_streams);
 }
 
-template <int NW, int SL, bool STATS>
+template <int NW, int SL>
 static void launch_parse4_variant(EncStream *d_streams, int n, cudaStream_t st) {
     typedef ParseShared4<NW - 1, SL> Sh;
     static_assert(sizeof(Sh) <= 227 * 1024, "stage A v4: shared memory exceeds an SM");
-    static bool attr_set = false;
-    auto kern = orz_parse4_kernel<NW, SL, STATS>;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sh));
-        attr_set = true;
-    }
+    auto kern = orz_parse4_kernel<NW, SL, false>;
+    set_smem_attr(kern, sizeof(Sh));
     ORZ_LAUNCH(kern, n, NW * 32, sizeof(Sh), st, d_streams);
 }
 
-template <int NW, int K, bool PARK, bool STATS>
-static void launch_parse5_variant(EncStream *d_streams, int n, cudaStream_t st) {
-    // mailbox slots per builder: enough for the 192-position look-ahead cap (kLookahead5) whatever the builder count
-    constexpr int NBv = Parse5Dims<NW, 1, K, PARK>::NB;
-    constexpr int SLw = ((int)kLookahead5 + NBv - 1) / NBv;
-    constexpr int SL = SLw < 1 ? 1 : (SLw > 8 ? 8 : SLw);
-    typedef ParseShared5<Parse5Dims<NW, SL, K, PARK>::NB, SL> Sh;
-    static_assert(sizeof(Sh) <= 227 * 1024, "stage A v5: shared memory of CTA 0 exceeds an SM");
-    static bool attr_set = false;
-    auto kern = orz_parse5_kernel<NW, SL, K, PARK, STATS>;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sh));
-        attr_set = true;
-    }
-    if (K > 1) ORZ_LAUNCH_CLUSTER(kern, n * K, NW * 32, sizeof(Sh), st, K, d_streams);
-    else ORZ_LAUNCH(kern, n, NW * 32, sizeof(Sh), st, d_streams);
-}
-template <bool STATS>
-static void launch_parse5(EncStream *d_streams, int n, cudaStream_t st) {
-    const char *e;
-    const int k = (e = getenv("ORZ_B200_PARSE_CLUSTER")) ? atoi(e) : 1;
-    const bool park = (e = getenv("ORZ_B200_PARSE_PARK")) ? atoi(e) != 0 : true;
-    const int nw = (e = getenv("ORZ_B200_PARSE_WARPS")) ? atoi(e) : 32;
-    if (k == 8) park ? launch_parse5_variant<32, 8, true, STATS>(d_streams, n, st) : launch_parse5_variant<32, 8, false, STATS>(d_streams, n, st);
-    else if (k == 4) park ? launch_parse5_variant<32, 4, true, STATS>(d_streams, n, st) : launch_parse5_variant<32, 4, false, STATS>(d_streams, n, st);
-    else if (k == 2) park ? launch_parse5_variant<32, 2, true, STATS>(d_streams, n, st) : launch_parse5_variant<32, 2, false, STATS>(d_streams, n, st);
-    else if (nw == 16) park ? launch_parse5_variant<16, 1, true, STATS>(d_streams, n, st) : launch_parse5_variant<16, 1, false, STATS>(d_streams, n, st);
-    else park ? launch_parse5_variant<32, 1, true, STATS>(d_streams, n, st) : launch_parse5_variant<32, 1, false, STATS>(d_streams, n, st);
+template <int NW, int K, bool STATS>
+static void launch_parse7_variant(EncStream *d_streams, int n, cudaStream_t st) {
+    static_assert(sizeof(ParseShared7) <= 227 * 1024, "stage A v7: shared memory of CTA 0 exceeds an SM");
+    auto kern = orz_parse7_kernel<NW, K, STATS>;
+    set_smem_attr(kern, sizeof(ParseShared7));
+#ifndef ORZ_SIMT_EMU
+    if (K > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+#endif
+    if (K > 1) ORZ_LAUNCH_CLUSTER(kern, n * K, NW * 32, sizeof(ParseShared7), st, K, d_streams);
+    else ORZ_LAUNCH(kern, n, NW * 32, sizeof(ParseShared7), st, d_streams);
 }
 
-template <int NW, int K, int G, bool STATS>
-static void launch_parse6_variant(EncStream *d_streams, int n, cudaStream_t st) {
-    // mailbox slots per group: enough for the 192-position look-ahead cap (kLookahead5) whatever the group count
-    constexpr int NBv = Parse6Dims<NW, 1, K, true, G>::NB;
-    constexpr int SLw = ((int)kLookahead5 + NBv - 1) / NBv;
-    constexpr int SL = SLw < 1 ? 1 : (SLw > 8 ? 8 : SLw);
-    typedef ParseShared5<Parse6Dims<NW, SL, K, true, G>::NB, SL> Sh;
-    static_assert(sizeof(Sh) <= 227 * 1024, "stage A v6: shared memory of CTA 0 exceeds an SM");
-    static bool attr_set = false;
-    auto kern = orz_parse6_kernel<NW, SL, K, true, G, STATS>;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sh));
-        attr_set = true;
+// Library configuration, read once per process:
+//   ORZ_B200_STATS=1            stage A v7 runs its instrumented instantiation (counters + clock64 phases, printed by capi.cu)
+//   ORZ_B200_V7_CLUSTER=1|8|16  CTAs per stream of stage A v7 (default 8)
+//   ORZ_B200_LEGACY_STAGE_A=1|v3|v3s|v4   ring-record layout instead of key lists (capi.cu reads it when a batch is created);
+//                               v3 / v3s / v4 additionally pin the kernel (tests)
+struct LibCfg {
+    bool stats;
+    int cluster;
+    int legacy; // 0 automatic, 3 = v3<22,16>, 13 = v3<11,8>, 4 = v4<16,4>
+    LibCfg() {
+        stats = getenv("ORZ_B200_STATS") != nullptr;
+        const char *e = getenv("ORZ_B200_V7_CLUSTER");
+        cluster = e ? atoi(e) : 8;
+        e = getenv("ORZ_B200_LEGACY_STAGE_A");
+        legacy = 0;
+        if (e && !strcmp(e, "v3")) legacy = 3;
+        else if (e && !strcmp(e, "v3s")) legacy = 13;
+        else if (e && !strcmp(e, "v4")) legacy = 4;
     }
-    if (K > 1) ORZ_LAUNCH_CLUSTER(kern, n * K, NW * 32, sizeof(Sh), st, K, d_streams);
-    else ORZ_LAUNCH(kern, n, NW * 32, sizeof(Sh), st, d_streams);
+};
+static const LibCfg &lib_cfg() {
+    static const LibCfg c;
+    return c;
 }
-template <int G, bool STATS>
-static void launch_parse6(EncStream *d_streams, int n, cudaStream_t st) {
-    const char *e;
-    const int k = (e = getenv("ORZ_B200_PARSE_CLUSTER")) ? atoi(e) : 1;
-    const int nw = (e = getenv("ORZ_B200_PARSE_WARPS")) ? atoi(e) : 32;
-    if (k == 8 && G >= 8) launch_parse6_variant<32, (G >= 8 ? 8 : 4), G, STATS>(d_streams, n, st); // (G = 4: 8 CTAs of 4-lane groups would not fit the mailbox)
-    else if (k >= 4) launch_parse6_variant<32, 4, G, STATS>(d_streams, n, st);
-    else if (k == 2) launch_parse6_variant<32, 2, G, STATS>(d_streams, n, st);
-    else if (nw == 16) launch_parse6_variant<16, 1, G, STATS>(d_streams, n, st);
-    else if (nw == 8) launch_parse6_variant<8, 1, G, STATS>(d_streams, n, st);
-    else launch_parse6_variant<32, 1, G, STATS>(d_streams, n, st);
-}
+bool parse7_stats_enabled() { return lib_cfg().stats; }
 
-void launch_parse(EncStream *d_streams, int n, cudaStream_t st) {
-    // One stream: v4 (parse_v4.cuh: windowed warp resolver + lock-free builders; measured on a B200, enwik8 -l2:
-    // 5.56 MB/s with 16 warps, 4.59 with 32, v3 4.18).  Several streams: v3, whose many-stream behaviour is the
-    // measured one.  ORZ_B200_PARSE=3|4 forces a version, ORZ_B200_PARSE_WARPS=8|16|32 the v4 block size.
-    const char *ver = getenv("ORZ_B200_PARSE");
-    const int pv = ver ? atoi(ver) : (n == 1 ? 4 : 3);
-    if (pv == 6) { // parse_v6.cuh: v5 (parked warps) with G-lane builder groups, ORZ_B200_PARSE_GROUP=4|8|16
-        const char *ge = getenv("ORZ_B200_PARSE_GROUP");
-        const int g = ge ? atoi(ge) : 8;
-        const bool st6 = getenv("ORZ_B200_STATS") != nullptr;
-        if (g == 16) st6 ? launch_parse6<16, true>(d_streams, n, st) : launch_parse6<16, false>(d_streams, n, st);
-        else if (g == 4) st6 ? launch_parse6<4, true>(d_streams, n, st) : launch_parse6<4, false>(d_streams, n, st);
-        else st6 ? launch_parse6<8, true>(d_streams, n, st) : launch_parse6<8, false>(d_streams, n, st);
-        return;
-    }
-    if (pv == 5) { // parse_v5.cuh: v4 + cluster builders (ORZ_B200_PARSE_CLUSTER=1|2|4|8), parked warps (ORZ_B200_PARSE_PARK), sleeping idle builders
-        if (getenv("ORZ_B200_STATS")) launch_parse5<true>(d_streams, n, st);
-        else launch_parse5<false>(d_streams, n, st);
-        return;
-    }
-    if (pv == 4) {
-        const char *w = getenv("ORZ_B200_PARSE_WARPS");
-        const int nw = w ? atoi(w) : 16;
-        const bool stats4 = getenv("ORZ_B200_STATS") != nullptr;
-        if (nw == 32) {
-            if (stats4) launch_parse4_variant<32, 4, true>(d_streams, n, st);
-            else launch_parse4_variant<32, 4, false>(d_streams, n, st);
-        } else if (nw == 8) {
-            if (stats4) launch_parse4_variant<8, 4, true>(d_streams, n, st);
-            else launch_parse4_variant<8, 4, false>(d_streams, n, st);
+// Stage A.  v7: the stream arena holds key lists (parse_v7.cuh: one cluster per stream).  Otherwise ring records +
+// hash chains: one stream runs v4 (windowed resolver, 16 warps), several streams run the v3 kernel (one executor thread + 8 or
+// 16 builder warps per stream), whose many-stream throughput is the measured one.
+void launch_parse(EncStream *d_streams, int n, bool v7, cudaStream_t st) {
+    const LibCfg &c = lib_cfg();
+    if (v7) {
+        if (c.stats) {
+            if (c.cluster == 16) launch_parse7_variant<16, 16, true>(d_streams, n, st);
+            else if (c.cluster == 1) launch_parse7_variant<16, 1, true>(d_streams, n, st);
+            else launch_parse7_variant<16, 8, true>(d_streams, n, st);
         } else {
-            if (stats4) launch_parse4_variant<16, 4, true>(d_streams, n, st);
-            else launch_parse4_variant<16, 4, false>(d_streams, n, st);
+            if (c.cluster == 16) launch_parse7_variant<16, 16, false>(d_streams, n, st);
+            else if (c.cluster == 1) launch_parse7_variant<16, 1, false>(d_streams, n, st);
+            else launch_parse7_variant<16, 8, false>(d_streams, n, st);
         }
         return;
     }
-    // few streams: 16 builders hide more latency per stream; many streams: 8 builders, more streams per SM
-    const char *force = getenv("ORZ_B200_PARSE_BUILDERS");
-    const int nb = force ? atoi(force) : (n <= 2 * 148 ? 16 : 8);
-    const bool stats = getenv("ORZ_B200_STATS") != nullptr; // counters and clock64 probes only in the instrumented build
-    if (nb == 16) {
-        if (stats) launch_parse_variant<22, 16, true>(d_streams, n, st);
-        else launch_parse_variant<22, 16, false>(d_streams, n, st);
-    } else {
-        if (stats) launch_parse_variant<11, 8, true>(d_streams, n, st);
-        else launch_parse_variant<11, 8, false>(d_streams, n, st);
+    if (c.legacy == 4 || (c.legacy == 0 && n == 1)) {
+        launch_parse4_variant<16, 4>(d_streams, n, st);
+        return;
     }
+    // few streams: 16 builders hide more latency per stream; many streams: 8 builders, more streams per SM
+    if (c.legacy == 3 || (c.legacy == 0 && n <= 2 * 148)) launch_parse_variant<22, 16>(d_streams, n, st);
+    else launch_parse_variant<11, 8>(d_streams, n, st);
 }
 void launch_emit(EncStream *d_streams, int n, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(orz_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitShared));
-        attr_set = true;
-    }
+    set_smem_attr(orz_emit_kernel, sizeof(EmitShared));
     ORZ_LAUNCH(orz_emit_kernel, n, kEmitThreads, sizeof(EmitShared), st, d_streams);
 }
+void launch_enc_advance(EncStream *d_streams, int n, cudaStream_t st) {
+    ORZ_LAUNCH(orz_enc_advance_kernel, 592, 256, 0, st, d_streams, n, 0);
+    ORZ_LAUNCH(orz_enc_advance_kernel, 592, 256, 0, st, d_streams, n, 1);
+    ORZ_LAUNCH(orz_enc_advance_done_kernel, (n + 63) / 64, 64, 0, st, d_streams, n);
+}
 void launch_enc_begin(EncStream *d_streams, int n, cudaStream_t st) { ORZ_LAUNCH(orz_enc_begin_kernel, n, 256, 0, st, d_streams); }
-void launch_enc_forward(EncStream *d_stream, uint32_t forward_len, cudaStream_t st) {
+void launch_enc_forward(EncStream *d_stream, uint32_t forward_len, bool v7, cudaStream_t st) {
+    if (v7) {
+        ORZ_LAUNCH(orz_enc7_forward_kernel, 592, 256, 0, st, d_stream, forward_len);
+        return;
+    }
     ORZ_LAUNCH(orz_enc_forward_kernel, 148, 256, 0, st, d_stream, forward_len, 0);
     ORZ_LAUNCH(orz_enc_forward_kernel, 148, 256, 0, st, d_stream, forward_len, 1);
 }

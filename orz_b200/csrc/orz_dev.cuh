@@ -144,9 +144,17 @@ struct EncStream {
     uint32_t items_cap;
     uint32_t depth0, depth1, depth2; // LZCfg (lz.rs:32-37)
     int32_t self_driven;  // 1: stream mode (kernel runs the lib.rs loop), 0: chunk mode (host drives)
+    // stage A v7 (parse_v7.cuh): per-key candidate lists instead of ring records + hash chains
+    uint2 *klist;         // [256 * kHeadsStride][64] circular candidate lists: pos | expected, bucket ordinal
+    uint32_t *kcnt;       // [256 * kHeadsStride] entries ever appended to the list
+    uint8_t *lm;          // [256][kNodesStride] match_len_min of the node in each ring slot (matcher.rs:231-237)
+    uint32_t *gext;       // [512][48] candidate positions of the probe records in flight
+    uint32_t v7;          // 1: this stream uses the v7 layout (nodes / heads are not allocated)
+    uint32_t need_slide;  // set by the emit kernel at the end of a block: the advance kernels slide, forward and load
     uint32_t dbg_flags;   // measurement switches (ORZ_B200_DBG): 1 no re-stamp, 8 executor cycle counters, 32 builder counters, 64 v3 idle builders sleep
     // mutable
     uint32_t bhead[kNumBuckets];
+    uint32_t bcnt[kNumBuckets];  // v7: inserts into each bucket so far (ring head = bcnt % 4094)
     uint32_t ctx_count[kNumCtx];
     uint32_t spos, sbuf_len, after_literal, first_block, n_items;
     uint32_t payload_len;
@@ -154,6 +162,7 @@ struct EncStream {
     int32_t status;       // 0 running, 1 done, <0 error code
     uint32_t n_chunks;
     unsigned long long dbg[8]; // stage A counters: steps, executor spin iterations (own / lazy1 / lazy2 probe), builds, aborted builds
+    unsigned long long dbg7[8]; // v7 resolver cycles: total, load, walk, hand-over, repair, wait; repairs by cause
 };
 
 // Per-stream decoder control block (lz.rs:348-357 LZDecoder, lib.rs:99-127 loop state)

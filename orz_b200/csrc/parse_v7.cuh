@@ -1,0 +1,797 @@
+// parse_v7.cuh — stage A, round-2 formulation (included by encode_kernels.cu; the default for few streams).
+//
+// lz.rs:131-235 is one serial chain per stream: which positions become ring nodes depends on every earlier decision.
+// v3..v6 (round 1) kept the reference's ring + hash-chain layout in HBM, walked it from builder warps and let the warp
+// that owns the chain also write every ring record, head, item and log entry — 1180 SM cycles per step on a B200
+// against 490 for one host core.  This formulation changes the data layout and the split of work:
+//
+//  * PER-KEY CANDIDATE LISTS instead of hash chains.  The candidates of find_match / has_lazy_match at position y are
+//    the ring nodes of bucket c = hash1(y-1) whose hash entry is e = hash_dword(y) % 4627, newest first
+//    (matcher.rs:135-228).  In the reference they are reached by one dependent load per hop (heads -> nexts -> nexts);
+//    a chain hop that lands on a re-used ring slot stops the walk ("positions strictly decrease", matcher.rs:176-179) or,
+//    for a stale `heads` entry, walks nodes of other hash entries whose first dword differs from y's and which therefore can
+//    never be taken nor trigger an early exit.  So the walk's RESULT is exactly: the nodes of key (c,e) that are still
+//    among the bucket's last 4094 inserts and whose position survived `forward`, newest first, the first `depth` of them.
+//    Here every key owns a 64-entry circular list in HBM (position, expected length, insert ordinal of the bucket); a
+//    node is alive iff  bucket_inserts_now - 1 - ordinal <= 4093.  A builder fetches all candidates of a position with
+//    ONE gather, not a chain of dependent loads, and nothing has to be re-linked when a slot is re-used.
+//    (match_len_min, the only mutable per-node field, lives in a byte array indexed by ring slot; it never influences the
+//    path, only the emitted length code, so only the committer touches it.)
+//
+//  * A CLUSTER per stream.  CTA 0 holds, in shared memory, a ring of PROBE RECORDS for the next 512 positions, `words`,
+//    the per-bucket insert counts and a log of recent steps.  All other CTAs of the cluster are BUILDERS: warp b builds
+//    the record of every position y = b (mod NBW) ahead of the parse — static fields, candidate gather, LCPs, the
+//    ballot-resolved semantics of matcher.rs:135-192 and the two lazy maxima — against the state committed up to a
+//    frontier F, and stores it into CTA 0's ring through DSMEM.
+//
+//  * The RESOLVER (warp 0 of CTA 0) does nothing but decide.  Lane l owns position spos+l.  A record built at
+//    frontier F is exact at the moment its position is decided iff no step in [F, now) has the same key (a 4096-entry
+//    "last step with this key hash" table answers that with one shared load) and its oldest candidate is still alive.
+//    The walk through the window costs one shuffle round per step; every lane keeps its decision inputs current by
+//    folding the broadcast step (bucket insert count -> robitlen<8, words update -> last_word_matched, same key -> stale).
+//    Decided steps go into a shared-memory queue; a stale record is repaired in place (REPAIR: the committed state is
+//    drained and the record rebuilt at frontier = now).
+//
+//  * The COMMITTER (warp 1 of CTA 0) drains the queue 32 steps at a time: list appends, lenmin bumps with the
+//    reference's in-order semantics (matcher.rs:62-80), items (lz.rs:173-236), and publishes the new frontier.
+//    None of its HBM latency is on the chain.
+//
+// All citations are file:line into richox/orz @29414c6.
+#pragma once
+#ifndef ORZ_SIMT_EMU
+#include <cooperative_groups.h>
+#endif
+
+#ifdef ORZ_SIMT_EMU
+#include <cstdio>
+#define V7_TRACE(...)                                              \
+    do {                                                           \
+        if (getenv("ORZ_V7_TRACE")) fprintf(stderr, __VA_ARGS__);  \
+    } while (0)
+#else
+#define V7_TRACE(...) ((void)0)
+#endif
+
+namespace orz {
+
+constexpr int kListCap = 64;           // entries per key list (circular, newest at (count-1) % 64)
+constexpr int kMaxDepth7 = 48;         // deepest LZCfg depth this kernel handles (levels 0-2 use 45)
+constexpr int kRing7 = 512;            // probe records kept in CTA 0's shared memory (positions)
+constexpr uint32_t kLead7 = kRing7 - 64; // builders stay this close to the parse position
+constexpr int kExtCand = 48;           // candidates per record kept for repairs
+constexpr int kSumWords = 12;          // summary words per record
+constexpr int kExtWords = 2 + kExtCand; // F_ext, ord0, candidates
+constexpr int kQueue7 = 512;           // step queue / recent-step log entries
+constexpr uint32_t kOrdMask = 0x7fffffffu;
+constexpr uint32_t kTyLit = 0, kTyWord = 1, kTyMatch = 2;
+
+// A key list entry: pos:25 | expected(low 7 bits):7  ,  ordinal:31 | expected(bit 7):1
+__device__ __forceinline__ uint2 kentry_make(uint32_t pos, uint32_t exp, uint32_t ord) {
+    return make_uint2((pos & 0x1ffffffu) | (exp & 0x7fu) << 25, (ord & kOrdMask) | (exp >> 7) << 31);
+}
+__device__ __forceinline__ uint32_t kentry_pos(uint2 e) { return e.x & 0x1ffffffu; }
+__device__ __forceinline__ uint32_t kentry_exp(uint2 e) { return (e.x >> 25) | (e.y >> 31) << 7; }
+__device__ __forceinline__ uint32_t kentry_ord(uint2 e) { return e.y & kOrdMask; }
+
+#ifdef ORZ_SIMT_EMU
+template <class T>
+__device__ __forceinline__ T *map_to_cta0(T *p) { return reinterpret_cast<T *>(simt::cur->cluster_smem[0] + (reinterpret_cast<uint8_t *>(p) - simt::cur->dyn_smem)); }
+__device__ __forceinline__ void cluster_barrier() { simt::cluster_sync(); }
+__device__ __forceinline__ unsigned cluster_cta_rank() { return simt::cur->cta_rank; }
+#else
+template <class T>
+__device__ __forceinline__ T *map_to_cta0(T *p) { return cooperative_groups::this_cluster().map_shared_rank(p, 0); }
+__device__ __forceinline__ void cluster_barrier() { cooperative_groups::this_cluster().sync(); }
+__device__ __forceinline__ unsigned cluster_cta_rank() { return cooperative_groups::this_cluster().block_rank(); }
+#endif
+
+// cluster-scope acquire / release on generic addresses (CTA 0's shared memory seen from any CTA of the cluster)
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+#ifdef ORZ_SIMT_EMU
+    return *p;
+#else
+    uint32_t v;
+    asm volatile("ld.acquire.cluster.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+#ifdef ORZ_SIMT_EMU
+    *p = v;
+#else
+    asm volatile("st.release.cluster.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ uint2 ldcg_u2(const uint2 *p) {
+#ifdef ORZ_SIMT_EMU
+    return *p;
+#else
+    return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ uint32_t ldcg_u32(const uint32_t *p) {
+#ifdef ORZ_SIMT_EMU
+    return *p;
+#else
+    return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ uint32_t ldcg_u8(const uint8_t *p) {
+#ifdef ORZ_SIMT_EMU
+    return *p;
+#else
+    return (uint32_t)__ldcg(p);
+#endif
+}
+
+struct ParseShared7 {
+    uint16_t words[32768];                  // lz.rs:52 — resolver only
+    uint32_t sum[kRing7][kSumWords];        // probe summaries, record of position y at y % 512
+    uint32_t ext[kRing7][kExtWords];        // per record: F_ext, ord0, then lcp | expected << 8 | (ord0 - ord) << 16 per candidate
+    uint4 queue[kQueue7];                   // decided steps: resolver -> committer; the tail doubles as the recent-step log
+    uint32_t lastkey[4096];                 // position of the latest decided step whose key hashes here (0 = none in this launch)
+    uint32_t bcnt[kNumBuckets];             // inserts into the bucket decided so far (ordinal of the next insert)
+    uint32_t cnt[kNumCtx];                  // committer: items per rank-coder context in this chunk
+    uint32_t spos;                          // parse position (resolver -> builders)
+    uint32_t fpos;                          // every step at a position < fpos is committed to HBM (committer -> builders)
+    uint32_t qhead;                         // steps queued (resolver)
+    uint32_t qdone;                         // steps committed (committer)
+    uint32_t done;
+    uint32_t pad[3];
+};
+
+// summary words
+//  0  stamp: the position the record describes (written last, with release semantics)
+//  1  key = c << 13 | e   | ncand << 21 (candidates considered, <= 48) | flags << 27 (bit 0: incomplete, must be rebuilt)
+//  2  hash2(y-1) | bytes(y, y+1) << 15
+//  3  fm_len | lazy max over depth1 << 8 | lazy max over depth2 << 16 | expected of the matched node << 24
+//  4  ordinal of the matched node
+//  5  ordinal of the oldest candidate considered
+//  6  F: the record is exact for every decision time T >= F as long as no step in [F, T) has its key
+//  7  words update if a literal is emitted here: hash2 index | value << 15   (lz.rs:233)
+//  8  words update if the match is emitted here                               (lz.rs:208)
+
+struct FmState {
+    int max_len;
+    uint32_t exp_best;
+    int best;     // candidate index of the best node so far
+    bool done;
+};
+
+// One round (32 candidates in chain order, lane = order) of matcher.rs:149-181.  `probe_eq(max_len)` is evaluated by the
+// lanes whose candidate cannot improve but whose probe dword (matcher.rs:150-153) may still match, which lets
+// matcher.rs:165-167 break on them.
+template <class ProbeEq>
+__device__ __forceinline__ void fm_round(FmState &st, bool valid, int lcp, uint32_t exp, int cand, int lane, ProbeEq probe_eq) {
+    if (st.done) return;
+    int cur = -1;
+    for (;;) {
+        const unsigned after = (cur >= 31) ? 0u : (0xffffffffu << (cur + 1));
+        const unsigned upd = __ballot_sync(kFull, valid && lcp > st.max_len) & after;
+        const int u = upd ? (__ffs(upd) - 1) : 32;
+        unsigned brk = __ballot_sync(kFull, valid && st.exp_best > 0 && lcp < st.max_len - 3 && lcp > (int)st.exp_best) & after;
+        if (u < 32) brk &= (1u << u) - 1u;
+        if (brk) {
+            bool eq = false;
+            if ((brk >> lane) & 1u) eq = probe_eq(st.max_len);
+            if (__ballot_sync(kFull, eq)) {
+                st.done = true;
+                return;
+            }
+        }
+        if (u >= 32) return;
+        st.max_len = __shfl_sync(kFull, lcp, u);
+        st.exp_best = __shfl_sync(kFull, exp, u);
+        st.best = __shfl_sync(kFull, cand, u);
+        if (st.max_len == kMatchMax || (st.exp_best > 0 && st.max_len > (int)st.exp_best)) { // matcher.rs:162-167
+            st.done = true;
+            return;
+        }
+        cur = u;
+    }
+}
+
+// lz.rs:146-236 for one position: what the step does given the match, the lazy maxima of the two next positions, the
+// last_word_matched bit and robitlen < 8.  Returns advance | type << 8.
+__device__ __forceinline__ uint32_t decide7(uint32_t mlen, uint32_t lz1, uint32_t lz2, uint32_t lwm, uint32_t rb, bool can_word) {
+    int lazy_id = 0;
+    if (mlen > 0) {
+        if (mlen < (uint32_t)(kMatchMax / 2)) {            // lz.rs:151
+            const uint32_t l1 = mlen + 1 + rb, l2 = l1 - lwm; // lz.rs:152-153
+            if (lz1 >= l1) lazy_id = 1;
+            else if (lz2 >= l2) lazy_id = 2;
+        }
+        if (lazy_id == 0) return mlen | kTyMatch << 8;
+    }
+    if (can_word && lazy_id != 1 && lwm) return 2u | kTyWord << 8; // lz.rs:218
+    return 1u | kTyLit << 8;
+}
+
+struct Build7 {
+    const uint8_t *win;
+    const uint2 *klist;
+    const uint32_t *kcnt;
+    uint32_t *gext;       // [kRing7][kExtCand] candidate positions (HBM), for byte probes during repairs
+    uint32_t sbuf_len;
+    int depth0, depth1, depth2;
+};
+
+// Builds the record of position y against the state committed below frontier F.  `gc` = a lower bound of the bucket's
+// insert count at the time y is decided.  Writes summary + ext through `sum`/`ext` (local or DSMEM pointers) and
+// publishes the stamp last.  Warp-cooperative.
+__device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint32_t F, const volatile uint32_t *bcnt_src, uint32_t *sum,
+                                              uint32_t *ext, int lane) {
+    const uint8_t *win = B.win;
+    const uint32_t prev4 = ld_u32_unaligned(win, y - 4); // bytes y-4 .. y-1
+    const uint32_t cur4 = ld_u32_unaligned(win, y);      // bytes y .. y+3
+    ORZ_COST(120);
+    const uint32_t b_m1 = prev4 >> 24, b_m2 = (prev4 >> 16) & 0xffu, b_m3 = (prev4 >> 8) & 0xffu, b_m4 = prev4 & 0xffu;
+    const uint32_t c = (b_m1 & 0x7fu) | is_alnum(b_m2) << 7;                          // hash1(y-1)  lz.rs:481-486
+    const uint32_t h2 = (b_m1 & 0x7fu) | ((b_m2 & 0x7fu) | is_alnum(b_m3) << 7) << 7; // hash2(y-1)  lz.rs:488-492
+    const uint32_t e0 = hash_dword(cur4) % kHashSize;                                  // matcher.rs:136
+    const uint32_t kidx = c * kHeadsStride + e0;
+    const uint32_t gc = bcast0(ld_vol_u32(&bcnt_src[c]));
+    const uint32_t cnt = bcast0(ldcg_u32(&B.kcnt[kidx]));
+    const uint32_t avail = cnt < (uint32_t)kListCap ? cnt : (uint32_t)kListCap;
+    int dmax = B.depth0 > B.depth1 ? B.depth0 : B.depth1;
+    dmax = dmax > B.depth2 ? dmax : B.depth2;
+    const uint2 *kl = B.klist + (size_t)kidx * kListCap;
+    ORZ_COST(450);
+
+    // entries newest first: t = 0 is entry (cnt-1) % 64.  The first r of them may already belong to steps at or after F
+    // (committed while this build runs): they are not part of the state "below F".
+    uint2 en = make_uint2(0, 0);
+    bool have = (uint32_t)lane < avail;
+    if (have) en = ldcg_u2(&kl[(cnt - 1 - (uint32_t)lane) % kListCap]);
+    ORZ_COST(450);
+    // the entries at or above the frontier must form a prefix (newest first); anything else means the list was appended
+    // to (and a slot re-used) while it was being read: the record is marked incomplete and rebuilt by a repair
+    const unsigned rm = __ballot_sync(kFull, have && kentry_pos(en) >= F);
+    const uint32_t r = rm == 0xffffffffu ? 32u : (uint32_t)(__ffs(~rm) - 1);
+    bool incomplete = r < 32u && (rm >> r) != 0u;
+    if (r > 0 && !incomplete) {
+        if (r >= 32 || r + (uint32_t)dmax > (uint32_t)(kListCap - 8)) incomplete = true;
+        else {
+            have = r + (uint32_t)lane < avail;
+            if (have) en = ldcg_u2(&kl[(cnt - 1 - r - (uint32_t)lane) % kListCap]);
+            ORZ_COST(450);
+            if (__ballot_sync(kFull, have && kentry_pos(en) >= F)) incomplete = true;
+        }
+    }
+    // alive: position survived forward (pos > 0), still among the bucket's last 4094 inserts, below the frontier
+    bool ok0 = !incomplete && have && lane < dmax && kentry_pos(en) != 0 && ((gc - 1 - kentry_ord(en)) & kOrdMask) <= (uint32_t)(kRing - 1);
+    // candidates form a prefix (positions and ordinals decrease along the list)
+    unsigned okm0 = __ballot_sync(kFull, ok0);
+    int n0 = okm0 == 0xffffffffu ? 32 : (__ffs(~okm0) - 1);
+    ok0 = lane < n0;
+    // second round: candidates 32..47
+    uint2 en1 = make_uint2(0, 0);
+    bool ok1 = false;
+    int n1 = 0;
+    if (n0 == 32 && dmax > 32 && !incomplete) {
+        const uint32_t t = r + 32u + (uint32_t)lane;
+        bool have1 = t < avail && 32 + lane < dmax;
+        if (have1) en1 = ldcg_u2(&kl[(cnt - 1 - t) % kListCap]);
+        ORZ_COST(450);
+        if (__ballot_sync(kFull, have1 && kentry_pos(en1) >= F)) incomplete = true;
+        ok1 = !incomplete && have1 && kentry_pos(en1) != 0 && ((gc - 1 - kentry_ord(en1)) & kOrdMask) <= (uint32_t)(kRing - 1);
+        const unsigned okm1 = __ballot_sync(kFull, ok1);
+        n1 = okm1 == 0xffffffffu ? 32 : (__ffs(~okm1) - 1);
+        ok1 = lane < n1;
+    }
+    if (incomplete) {
+        ok0 = ok1 = false;
+        n0 = n1 = 0;
+    }
+    const int ncand = n0 + n1;
+    const uint32_t p0 = kentry_pos(en), p1 = kentry_pos(en1);
+    int lcp0 = -1, lcp1 = -1;
+    if (ok0) lcp0 = lcp_win_win(win, p0, y);
+    if (ok1) lcp1 = lcp_win_win(win, p1, y);
+    ORZ_COST(500);
+    // lazy maxima (matcher.rs:194-228 restated: has_lazy_match(min_len) <=> longest LCP among the first `depth` nodes >= min_len)
+    int m1 = warp_max(max((ok0 && lane < B.depth1) ? lcp0 : -1, (ok1 && 32 + lane < B.depth1) ? lcp1 : -1));
+    int m2 = warp_max(max((ok0 && lane < B.depth2) ? lcp0 : -1, (ok1 && 32 + lane < B.depth2) ? lcp1 : -1));
+    // find_match (matcher.rs:135-192)
+    FmState st;
+    st.max_len = kMatchMin - 1;
+    st.exp_best = kMatchMin;
+    st.best = -1;
+    st.done = B.depth0 <= 0;
+    fm_round(st, ok0 && lane < B.depth0, lcp0, kentry_exp(en), lane, lane,
+             [&](int ml) { return ld_u32_unaligned(win, p0 + ml - 3) == ld_u32_unaligned(win, y + ml - 3); });
+    if (n1 > 0)
+        fm_round(st, ok1 && 32 + lane < B.depth0, lcp1, kentry_exp(en1), 32 + lane, lane,
+                 [&](int ml) { return ld_u32_unaligned(win, p1 + ml - 3) == ld_u32_unaligned(win, y + ml - 3); });
+    uint32_t mlen = 0, wexp = 0, word = 0;
+    if (st.max_len >= kMatchMin && y + (uint32_t)st.max_len < B.sbuf_len && st.best >= 0) { // matcher.rs:183
+        mlen = (uint32_t)st.max_len;
+        const uint32_t bo0 = __shfl_sync(kFull, kentry_ord(en), st.best & 31), bo1 = __shfl_sync(kFull, kentry_ord(en1), st.best & 31);
+        const uint32_t be0 = __shfl_sync(kFull, kentry_exp(en), st.best & 31), be1 = __shfl_sync(kFull, kentry_exp(en1), st.best & 31);
+        word = st.best < 32 ? bo0 : bo1;
+        wexp = st.best < 32 ? be0 : be1;
+    }
+    const uint32_t ord0 = bcast0(kentry_ord(en));
+    const int last = ncand - 1;
+    const uint32_t lo0 = __shfl_sync(kFull, kentry_ord(en), last >= 0 ? (last & 31) : 0), lo1 = __shfl_sync(kFull, kentry_ord(en1), last >= 0 ? (last & 31) : 0);
+    const uint32_t ordmin = last < 0 ? 0u : (last < 32 ? lo0 : lo1);
+    // words updates of the two possible outcomes (lz.rs:208,233): words[hash2(s'-3)] = bytes s'-2, s'-1
+    const uint32_t hw_lit = (b_m2 & 0x7fu) | ((b_m3 & 0x7fu) | is_alnum(b_m4) << 7) << 7; // s' = y+1
+    const uint32_t wv_lit = b_m1 | (cur4 & 0xffu) << 8;
+    uint32_t hw_m = 0, wv_m = 0;
+    if (mlen > 0) { // s' = y + len
+        const uint32_t t4 = ld_u32_unaligned(win, y + mlen - 5); // bytes s'-5 .. s'-2
+        const uint32_t t2 = ld_u32_unaligned(win, y + mlen - 2); // bytes s'-2 .. s'+1
+        const uint32_t x3 = (t4 >> 16) & 0xffu, x4 = (t4 >> 8) & 0xffu, x5 = t4 & 0xffu;
+        hw_m = (x3 & 0x7fu) | ((x4 & 0x7fu) | is_alnum(x5) << 7) << 7;
+        wv_m = t2 & 0xffffu;
+    }
+    ORZ_COST(200);
+    // ---- publish: ext (all lanes), summary words 1.. (lane 0), fence, stamp
+    if (ok0) ext[2 + lane] = (uint32_t)lcp0 | kentry_exp(en) << 8 | ((ord0 - kentry_ord(en)) & 0xfffu) << 16;
+    if (ok1 && 32 + lane < kExtCand) ext[2 + 32 + lane] = (uint32_t)lcp1 | kentry_exp(en1) << 8 | ((ord0 - kentry_ord(en1)) & 0xfffu) << 16;
+    uint32_t *gx = B.gext + (size_t)(y % kRing7) * kExtCand;
+    if (ok0) gx[lane] = p0;
+    if (ok1 && 32 + lane < kExtCand) gx[32 + lane] = p1;
+    if (lane == 0) {
+        const uint32_t c1 = m1 < 0 ? 0u : (m1 > 255 ? 255u : (uint32_t)m1);
+        const uint32_t c2 = m2 < 0 ? 0u : (m2 > 255 ? 255u : (uint32_t)m2);
+        ext[0] = F;
+        ext[1] = ord0;
+        sum[1] = (c << 13 | e0) | (uint32_t)ncand << 21 | (incomplete ? 1u : 0u) << 27;
+        sum[2] = h2 | (cur4 & 0xffffu) << 15;
+        sum[3] = mlen | c1 << 8 | c2 << 16 | wexp << 24;
+        sum[4] = word;
+        sum[5] = ordmin;
+        sum[6] = F;
+        sum[7] = hw_lit | wv_lit << 15;
+        sum[8] = hw_m | wv_m << 15;
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release_u32(&sum[0], y);
+}
+
+// NW warps per CTA, K CTAs per stream (a thread-block cluster).  CTA 0: warp 0 resolver, warp 1 committer, the warps that
+// do not share the resolver's SM sub-partition build; CTAs 1..K-1: all warps build.
+template <int NW, int K>
+struct Dims7 {
+    static constexpr int NB0 = NW - 2 - (NW - 1) / 4 + ((NW - 1) / 4 > 0 ? 0 : 0); // builders in CTA 0: warps >= 2 with warp % 4 != 0
+    static constexpr int NBW = NB0 + (K - 1) * NW;
+};
+
+template <int NW, int K, bool STATS>
+__global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams) {
+    constexpr int NT = NW * 32;
+    EncStream *S = &streams[blockIdx.x / K];
+    const unsigned rank = K > 1 ? cluster_cta_rank() : 0u;
+    ORZ_DYN_SHARED(smem_raw);
+    ParseShared7 &shl = *reinterpret_cast<ParseShared7 *>(smem_raw);
+    ParseShared7 &sh = K > 1 ? *map_to_cta0(&shl) : shl; // CTA 0's shared memory (DSMEM for the other CTAs)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool active = S->status == 0; // uniform over the cluster (the status word is not written before the final barrier)
+
+    if (active && rank == 0) {
+        for (int i = tid; i < kNumCtx; i += NT) shl.cnt[i] = 0;
+        for (int i = tid; i < kNumBuckets; i += NT) shl.bcnt[i] = S->bcnt[i];
+        for (int i = tid; i < 4096; i += NT) shl.lastkey[i] = 0;
+        for (int i = tid; i < kRing7; i += NT) shl.sum[i][0] = kNone;
+        for (int i = tid; i < 32768 / 8; i += NT) reinterpret_cast<uint4 *>(shl.words)[i] = reinterpret_cast<const uint4 *>(S->words)[i];
+        if (tid == 0) {
+            shl.spos = S->spos;
+            shl.fpos = S->spos;
+            shl.qhead = 0;
+            shl.qdone = 0;
+            shl.done = 0;
+        }
+    }
+    __syncthreads();
+    if (K > 1) cluster_barrier(); // CTA 0's shared memory is initialised before any remote builder looks at it
+    if (active) {
+        const uint32_t sbuf_len = S->sbuf_len;
+        Build7 B;
+        B.win = S->win;
+        B.klist = S->klist;
+        B.kcnt = S->kcnt;
+        B.gext = S->gext;
+        B.sbuf_len = sbuf_len;
+        B.depth0 = (int)S->depth0;
+        B.depth1 = (int)S->depth1;
+        B.depth2 = (int)S->depth2;
+        volatile uint32_t *v_spos = &sh.spos;
+        volatile uint32_t *v_done = &sh.done;
+
+        if (rank == 0 && warp == 0) {
+            // ============================================================== resolver
+            volatile uint32_t *v_qhead = &shl.qhead;
+            volatile uint32_t *v_qdone = &shl.qdone;
+            const uint32_t items_cap = S->items_cap < kChunkItems ? S->items_cap : kChunkItems;
+            uint32_t spos = S->spos;
+            uint32_t after_literal = S->after_literal;
+            uint32_t n_items = 0, qhead = 0;
+            unsigned long long n_windows = 0, n_wait = 0, n_repair = 0, n_rep_conf = 0, n_rep_alive = 0, n_rep_inc = 0;
+            long long cyc_wait = 0, cyc_walk = 0, cyc_commit = 0, cyc_repair = 0, cyc_load = 0;
+            const long long t_begin = STATS ? clock64() : 0;
+            const unsigned lt_mask = (1u << lane) - 1u;
+            int wd_code = 0;
+            unsigned idle = 0;
+            while (spos < sbuf_len && n_items < items_cap) {
+                const long long t0 = STATS ? clock64() : 0;
+                const uint32_t x = spos + (uint32_t)lane;
+                uint32_t *rs = shl.sum[x % kRing7];
+                // ---- load this lane's record
+                const uint32_t stamp = ld_acquire_u32(&rs[0]);
+                const bool ready = stamp == x;
+                const uint4 a = *reinterpret_cast<const uint4 *>(&rs[0]);
+                const uint4 b = *reinterpret_cast<const uint4 *>(&rs[4]);
+                const uint32_t wmat = rs[8];
+                const unsigned rdy = __ballot_sync(kFull, ready);
+                if (lane == 0) V7_TRACE("R spos %u rdy %08x stamp %u\n", spos, rdy, stamp);
+                // a decision at lane l needs the records of l, l+1 and l+2
+                const uint32_t last_pos = sbuf_len + 1; // the last position that has a record
+                unsigned need0 = 0x7u;
+                if (spos + 1 > last_pos) need0 = 0x1u;
+                else if (spos + 2 > last_pos) need0 = 0x3u;
+                if ((rdy & need0) != need0) { // the next step's records are not there yet
+                    if (STATS) {
+                        n_wait++;
+                        cyc_wait += clock64() - t0;
+                    }
+                    if (++idle > 200000000u) {
+                        wd_code = 1;
+                        break;
+                    }
+                    ORZ_POLL();
+                    continue;
+                }
+                idle = 0;
+                const uint32_t key = a.y & 0x1fffffu, c = key >> 13;
+                const uint32_t ncand = (a.y >> 21) & 0x3fu;
+                const bool incomplete = (a.y >> 27) & 1u;
+                const uint32_t h2 = a.z & 0x7fffu, b2 = a.z >> 15;
+                const uint32_t mlen = a.w & 0xffu, lz1 = (a.w >> 8) & 0xffu, lz2 = (a.w >> 16) & 0xffu, wexp = a.w >> 24;
+                const uint32_t word = b.x, ordmin = b.y, F = b.z, wlit = b.w;
+                uint32_t lwe = shl.words[h2];                                  // lz.rs:132 (kept current below)
+                const uint32_t bc = shl.bcnt[c];
+                const uint32_t kh = (key ^ (key >> 9)) & 4095u;
+                const uint32_t lk = shl.lastkey[kh];
+                // exactness of the record at decision time (see the header): no step with this key since F, oldest candidate alive
+                const bool confl = lk >= F;
+                const int room = ncand == 0 ? 64 : (int)(kRing - 1) - (int)((bc - 1 - ordmin) & kOrdMask);
+                const bool st_bad = !ready || confl || incomplete || room < 0;
+                const bool tight = room < 32;
+                const uint32_t fl = (st_bad ? 1u : 0u) | (tight ? 2u : 0u) | (ready ? 4u : 0u);
+                const uint32_t fl1 = __shfl_down_sync(kFull, fl, 1), fl2 = __shfl_down_sync(kFull, fl, 2);
+                const uint32_t key1 = __shfl_down_sync(kFull, key, 1), key2 = __shfl_down_sync(kFull, key, 2);
+                const uint32_t lzn1 = __shfl_down_sync(kFull, lz1, 1), lzn2 = __shfl_down_sync(kFull, lz2, 2);
+                bool ownstale = st_bad || (lane > 0 && tight);
+                bool n1stale = lane >= 31 || (fl1 & 1u) || (lane > 0 && (fl1 & 2u));
+                bool n2stale = lane >= 30 || (fl2 & 1u) || (lane > 0 && (fl2 & 2u));
+                // records that are simply not built yet end the window instead of asking for a repair
+                const bool notready = !ready || (lane < 31 && !(fl1 & 4u) && x + 1 <= last_pos) || (lane < 30 && !(fl2 & 4u) && x + 2 <= last_pos);
+                const bool can_word = x + 1 < sbuf_len;
+                const bool lzneed = mlen > 0 && mlen < (uint32_t)(kMatchMax / 2);
+                // the four possible outcomes, indexed by last_word_matched * 2 + (robitlen < 8)
+                uint32_t nd = 0, nt = 0;
+#pragma unroll
+                for (uint32_t s = 0; s < 4; s++) {
+                    const uint32_t d = decide7(mlen, lzn1, lzn2, s >> 1, s & 1u, can_word);
+                    nd |= (d & 0xffu) << (8 * s);
+                    nt |= (d >> 8) << (2 * s);
+                }
+                const uint32_t ro0 = (bc - 1 - word) & kOrdMask; // reduced offset if no further insert precedes this step (matcher.rs:185)
+                uint32_t pend = 0;
+                // what this lane decided when its turn came
+                uint32_t my_ty = 0, my_d = 0, my_pend = 0, my_al = 0, my_lwe = 0;
+                bool onpath = false;
+                uint32_t cur = 0, nsteps = 0;
+                int stop = 0; // 1: repair needed at cur, 2: record not ready at cur
+                const long long t1 = STATS ? clock64() : 0;
+                if (STATS) cyc_load += t1 - t0;
+
+                // ---- walk the step chain through the window (lz.rs:131-236): one shuffle round per step
+                for (;;) {
+                    const uint32_t lwm = (lwe == b2) ? 1u : 0u;                        // lz.rs:133
+                    const uint32_t rb = (ro0 + pend < 510u) ? 1u : 0u;                 // robitlen < 8  <=>  reduced offset < 510
+                    const uint32_t sel = lwm * 2 + rb;
+                    const uint32_t d = (nd >> (8 * sel)) & 0xffu, ty = (nt >> (2 * sel)) & 3u;
+                    const uint32_t slow = notready ? 2u : ((ownstale || (lzneed && (n1stale || n2stale))) ? 1u : 0u);
+                    // type 3 = the window ends here: advance field 1 = repair needed, 2 = a record is not built yet
+                    const uint32_t pk = slow ? (slow | 3u << 8) : (d | ty << 8 | key << 10);   // key: 21 bits
+                    const uint32_t wu = ty == kTyWord ? 0xffffffffu : (ty == kTyMatch ? wmat : wlit);
+                    const uint32_t pk_s = __shfl_sync(kFull, pk, cur);
+                    const uint32_t wu_s = __shfl_sync(kFull, wu, cur);
+                    const uint32_t d_s = pk_s & 0xffu, ty_s = (pk_s >> 8) & 3u, key_s = pk_s >> 10;
+                    if (ty_s == 3u) {
+                        stop = (int)d_s;
+                        break;
+                    }
+                    if ((uint32_t)lane == cur) {
+                        onpath = true;
+                        my_ty = ty;
+                        my_d = d;
+                        my_pend = pend;
+                        my_al = after_literal;
+                        my_lwe = lwe;
+                    }
+                    nsteps++;
+                    after_literal = ty_s == kTyLit ? 1u : 0u;
+                    // keep every later lane's inputs current
+                    if ((uint32_t)lane > cur) {
+                        if ((key_s >> 13) == c) pend++;
+                        if (key_s == key) ownstale = true;
+                        if (key_s == key1) n1stale = true;
+                        if (key_s == key2) n2stale = true;
+                        if (wu_s != 0xffffffffu && (wu_s & 0x7fffu) == h2) lwe = wu_s >> 15;
+                    }
+                    cur += d_s;
+                    if (cur >= 30 || n_items + nsteps >= items_cap || spos + cur >= sbuf_len) break;
+                }
+                if (lane == 0) V7_TRACE("  walk nsteps %u cur %u stop %d mlen %u lz %u %u key %x F %u room %d fl %x\n", nsteps, cur, stop, mlen, lzn1, lzn2, key, F, room, fl);
+                const long long t2 = STATS ? clock64() : 0;
+                if (STATS) {
+                    cyc_walk += t2 - t1;
+                    n_windows++;
+                }
+
+                // ---- hand the decided steps to the committer and fold them into the shared tables
+                if (nsteps > 0) {
+                    // queue space: the committer must have passed the entries about to be overwritten
+                    while ((int)(qhead + nsteps - bcast0(ld_vol_u32(v_qdone))) > kQueue7 - 8) ORZ_POLL();
+                    const unsigned pm = __ballot_sync(kFull, onpath);
+                    const bool writes = onpath && my_ty != kTyWord;
+                    const uint32_t mywu = my_ty == kTyMatch ? wmat : wlit;
+                    if (onpath) {
+                        const uint32_t qi = qhead + (uint32_t)__popc(pm & lt_mask);
+                        const uint32_t ord = (bc + my_pend) & kOrdMask;
+                        uint4 rec;
+                        rec.x = x | my_ty << 25 | my_al << 27;
+                        rec.y = ord;
+                        rec.z = key | (my_ty == kTyMatch ? mlen : 0u) << 21;
+                        rec.w = my_ty == kTyMatch ? (((ro0 + my_pend) & 0xfffu) | wexp << 12 | (my_lwe & 0xffu) << 20)
+                                                  : ((b2 & 0xffu) | (my_lwe & 0xffu) << 20);
+                        shl.queue[qi % kQueue7] = rec;
+                        atomicAdd(&shl.bcnt[c], 1u);
+                        atomicMax(&shl.lastkey[kh], x);
+                    }
+                    { // lz.rs:208,233 — the last writer of an index wins
+                        const unsigned same = __match_any_sync(kFull, writes ? (mywu & 0x7fffu) : (0x10000u | (uint32_t)lane));
+                        if (writes && (same >> lane) <= 1u) shl.words[mywu & 0x7fffu] = (uint16_t)(mywu >> 15);
+                    }
+                    qhead += nsteps;
+                    n_items += nsteps;
+                    spos += cur;
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) {
+                        *v_qhead = qhead;
+                        *v_spos = spos;
+                    }
+                }
+                const long long t3 = STATS ? clock64() : 0;
+                if (STATS) cyc_commit += t3 - t2;
+                if (stop == 1 && spos < sbuf_len && n_items < items_cap) {
+                    // ---- REPAIR: the record of spos (or of a lazy neighbour it needs) is stale.  Drain the committer and rebuild
+                    // the records of spos, spos+1, spos+2 against the now fully committed state; the next window sees them exact.
+                    if (STATS) n_repair++;
+                    while (bcast0(ld_vol_u32(v_qdone)) != qhead) ORZ_POLL();
+                    __threadfence();
+                    for (uint32_t k = 0; k < 3; k++) {
+                        const uint32_t y = spos + k;
+                        if (y > last_pos) break;
+                        // only records that are built and stale; a record that is not there yet is left to its builder
+                        uint32_t *ys = shl.sum[y % kRing7];
+                        const uint32_t have_y = bcast0(ld_vol_u32(ys));
+                        if (have_y != y) continue;
+                        build_record7(B, y, spos, shl.bcnt, ys, shl.ext[y % kRing7], lane);
+                    }
+                    __syncwarp();
+                    if (STATS) cyc_repair += clock64() - t3;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                *v_done = 1;
+                if (wd_code) {
+                    S->status = -7;
+                    S->dbg[6] = (unsigned long long)wd_code;
+                    S->dbg[7] = spos;
+                }
+                S->spos = spos;
+                S->after_literal = after_literal;
+                S->n_items = n_items;
+                if (STATS) {
+                    S->dbg[0] += n_items;
+                    S->dbg[1] += n_windows;
+                    S->dbg[2] += n_wait;
+                    S->dbg[3] += n_repair;
+                    S->dbg7[0] += (unsigned long long)(clock64() - t_begin);
+                    S->dbg7[1] += (unsigned long long)cyc_load;
+                    S->dbg7[2] += (unsigned long long)cyc_walk;
+                    S->dbg7[3] += (unsigned long long)cyc_commit;
+                    S->dbg7[4] += (unsigned long long)cyc_repair;
+                    S->dbg7[5] += (unsigned long long)cyc_wait;
+                    S->dbg7[6] += n_rep_conf + n_rep_alive + n_rep_inc;
+                }
+            }
+        } else if (rank == 0 && warp == 1) {
+            // ============================================================== committer
+            volatile uint32_t *v_qhead = &shl.qhead;
+            volatile uint32_t *v_qdone = &shl.qdone;
+            Item *items = S->items;
+            uint2 *klist = S->klist;
+            uint32_t *kcnt = S->kcnt;
+            uint8_t *lmarr = S->lm;
+            uint32_t tail = 0;
+            const unsigned lt_mask = (1u << lane) - 1u;
+            for (;;) {
+                const uint32_t dn = bcast0(ld_vol_u32(v_done));
+                const uint32_t head = bcast0(ld_vol_u32(v_qhead));
+                if (head == tail) {
+                    if (dn) break;
+                    ORZ_POLL();
+                    continue;
+                }
+                const uint32_t n = head - tail < 32u ? head - tail : 32u;
+                if (lane == 0) V7_TRACE("C tail %u n %u\n", tail, n);
+                const bool act = (uint32_t)lane < n;
+                uint4 rec = make_uint4(0, 0, 0, 0);
+                if (act) rec = shl.queue[(tail + (uint32_t)lane) % kQueue7];
+                const uint32_t pos = rec.x & 0x1ffffffu, ty = (rec.x >> 25) & 3u, al = (rec.x >> 27) & 1u;
+                const uint32_t ord = rec.y, key = rec.z & 0x1fffffu, mlen = rec.z >> 21;
+                const uint32_t c = key >> 13, e = key & 0x1fffu;
+                const uint32_t ro = rec.w & 0xfffu, wexp = (rec.w >> 12) & 0xffu, unl = (rec.w >> 20) & 0xffu, byte = rec.w & 0xffu;
+                const bool is_m = act && ty == kTyMatch;
+                // ring slots: the insert goes to (head + 1) % 4094 where head = slot of the previous insert (matcher.rs:63,77);
+                // bucket insert number `ord` (0-based) therefore lands in slot (ord + 1) % 4094
+                const uint32_t slot = (ord + 1) % kRing;
+                const uint32_t mord = (ord - 1 - ro) & kOrdMask;
+                const uint32_t mslot = (mord + 1) % kRing;
+                const uint32_t wkey_ins = act ? (c << 12 | slot) : (0x80000000u | (uint32_t)lane);
+                const uint32_t wkey_m = is_m ? (c << 12 | mslot) : (0x40000000u | (uint32_t)lane);
+                // lenmin of the matched node as stored; the serial pass below applies the effects of earlier steps of this batch
+                uint32_t cur_lm = 0;
+                if (is_m) cur_lm = ldcg_u8(&lmarr[c * kNodesStride + mslot]);
+                const uint32_t kidx = c * kHeadsStride + e;
+                uint32_t kc = 0;
+                if (act) kc = ldcg_u32(&kcnt[kidx]);
+                ORZ_COST(450);
+                // matcher.rs:62-80 in step order: [bump the matched node's lenmin] then [write the new node, lenmin 0]
+                uint32_t new_lm = 0;     // value this lane's bump writes
+                bool bump = false;
+                bool ins_dead = false, bump_dead = false; // a later step of the batch overwrites the location
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t wm_i = __shfl_sync(kFull, wkey_m, i);
+                    const uint32_t wi_i = __shfl_sync(kFull, wkey_ins, i);
+                    uint32_t bv = 0xffffffffu;
+                    if ((uint32_t)lane == i && is_m && cur_lm <= mlen) {
+                        bump = true;
+                        new_lm = mlen + 1 < 127u ? mlen + 1 : 127u;
+                        bv = new_lm;
+                    }
+                    bv = __shfl_sync(kFull, bv, i);
+                    if ((uint32_t)lane > i) {
+                        if (bv != 0xffffffffu && wkey_m == wm_i) cur_lm = bv; // an earlier step bumped the node this lane matched
+                        if (wkey_m == wi_i) cur_lm = 0;                        // ... or it IS that step's new node
+                    }
+                    if ((uint32_t)lane < i) { // later writes to the same byte make this lane's stores dead
+                        if (wkey_ins == wi_i || (bv != 0xffffffffu && wkey_ins == wm_i)) ins_dead = true;
+                        if (bump && (wkey_m == wi_i || (bv != 0xffffffffu && wkey_m == wm_i))) bump_dead = true;
+                    }
+                    if ((uint32_t)lane == i && bump && wkey_m == wkey_ins) bump_dead = true; // matcher.rs:66-77: own insert overwrites it
+                }
+                // ---- items (lz.rs:173-236)
+                const uint32_t ctx = c | al << 8;
+                const unsigned same_ctx = __match_any_sync(kFull, act ? ctx : (0x10000u | (uint32_t)lane));
+                const uint32_t cbase = act ? shl.cnt[ctx] : 0u;
+                __syncwarp();
+                if (act) {
+                    Item it;
+                    it.ctx = (uint16_t)ctx;
+                    it.unlikely = (uint8_t)unl;
+                    it.pad = 0;
+                    it.seq = cbase + (uint32_t)__popc(same_ctx & lt_mask);
+                    if (ty == kTyMatch) {
+                        uint32_t roid, robitlen, robits;
+                        roid_encode(ro, roid, robitlen, robits);                    // lz.rs:148
+                        const uint32_t mexp = wexp > (uint32_t)kMatchMin ? wexp : (uint32_t)kMatchMin; // matcher.rs:187-188
+                        const uint32_t mmin = cur_lm > (uint32_t)kMatchMin ? cur_lm : (uint32_t)kMatchMin;
+                        uint32_t eml;                                               // lz.rs:173-177
+                        if (mlen > mexp) eml = mlen - mmin;
+                        else if (mlen < mexp) eml = mlen - mmin + 1;
+                        else eml = 0;
+                        eml &= 0xffu;
+                        const uint32_t lenid = eml < (uint32_t)(kLenidSize - 1) ? eml : (uint32_t)(kLenidSize - 1);
+                        it.symbol = (uint16_t)(256 + roid * kLenidSize + lenid);
+                        it.robits = (uint16_t)robits;
+                        it.robitlen = (uint8_t)robitlen;
+                        it.eml = (uint8_t)eml;
+                        it.flags = (uint8_t)(al | 2u);
+                    } else {
+                        it.symbol = ty == kTyWord ? (uint16_t)kWordSym : (uint16_t)byte;
+                        it.robits = 0;
+                        it.robitlen = 0;
+                        it.eml = 0;
+                        it.flags = (uint8_t)al;
+                    }
+                    items[tail + (uint32_t)lane] = it;
+                    if (!(same_ctx & ~lt_mask & ~(1u << lane))) shl.cnt[ctx] = cbase + (uint32_t)__popc(same_ctx); // group's last lane
+                    // ---- ring bytes
+                    if (bump && !bump_dead) lmarr[c * kNodesStride + mslot] = (uint8_t)new_lm;
+                    if (!ins_dead) lmarr[c * kNodesStride + slot] = 0;
+                }
+                // ---- key lists: append in step order
+                const unsigned same_k = __match_any_sync(kFull, act ? kidx : (0x80000000u | (uint32_t)lane));
+                if (act) {
+                    const uint32_t rk = (uint32_t)__popc(same_k & lt_mask);
+                    klist[(size_t)kidx * kListCap + (kc + rk) % kListCap] = kentry_make(pos, ty == kTyMatch ? mlen : 0u, ord);
+                }
+                __threadfence();
+                __syncwarp();
+                if (act && !(same_k & ~lt_mask & ~(1u << lane))) kcnt[kidx] = kc + (uint32_t)__popc(same_k);
+                __threadfence();
+                __syncwarp();
+                tail += n;
+                const uint32_t lastpos = __shfl_sync(kFull, pos, (int)n - 1);
+                if (lane == 0) {
+                    st_release_u32(&shl.fpos, lastpos + 1);
+                    *v_qdone = tail;
+                }
+                __syncwarp();
+            }
+        } else if (rank != 0 || (warp >= 2 && (warp & 3) != 0)) {
+            // ============================================================== builders
+            constexpr int NB0 = NW - 2 - (NW - 1) / 4;
+            constexpr int NBW = NB0 + (K - 1) * NW;
+            int bi;
+            if (rank == 0) bi = warp - 2 - warp / 4;
+            else bi = NB0 + ((int)rank - 1) * NW + warp;
+            unsigned long long nbuild = 0;
+            const uint32_t last_pos = sbuf_len + 1;
+            uint32_t y = S->spos;
+            y += ((uint32_t)bi + (uint32_t)NBW - y % (uint32_t)NBW) % (uint32_t)NBW; // first position >= spos owned by this builder
+            for (;;) {
+                if (bcast0(ld_vol_u32(v_done))) break;
+                const uint32_t sp = bcast0(ld_vol_u32(v_spos));
+                if (y < sp) y += ((sp - y + (uint32_t)NBW - 1) / (uint32_t)NBW) * (uint32_t)NBW; // the parse went past: skip
+                if (y > last_pos || y > sp + kLead7) {
+#ifdef ORZ_SIMT_EMU
+                    ORZ_POLL();
+#else
+                    __nanosleep(200);
+#endif
+                    continue;
+                }
+                const uint32_t F = bcast0(ld_acquire_u32(&sh.fpos));
+                if (lane == 0) V7_TRACE("B%d y %u F %u sp %u\n", bi, y, F, sp);
+                build_record7(B, y, F, sh.bcnt, sh.sum[y % kRing7], sh.ext[y % kRing7], lane);
+                if (STATS) nbuild++;
+                y += (uint32_t)NBW;
+            }
+            if (STATS && lane == 0) atomicAdd(&S->dbg[4], nbuild);
+        }
+    }
+    __syncthreads();
+    if (K > 1) cluster_barrier(); // no remote builder touches CTA 0's shared memory after this point
+    if (active && rank == 0) {
+        for (int i = tid; i < 32768 / 8; i += NT) reinterpret_cast<uint4 *>(S->words)[i] = reinterpret_cast<const uint4 *>(shl.words)[i];
+        for (int i = tid; i < kNumCtx; i += NT) S->ctx_count[i] = shl.cnt[i];
+        for (int i = tid; i < kNumBuckets; i += NT) S->bcnt[i] = shl.bcnt[i];
+    }
+}
+
+// lz.rs:82-87 for the key lists: positions are rebased, entries whose node died (matcher.rs:82-87,123-133: pos <= forward_len)
+// become pos 0, which ends a candidate list there.
+__device__ __forceinline__ void enc7_forward_rebase(uint2 *klist, const uint32_t *kcnt, uint32_t forward_len, size_t gid, size_t gsz) {
+    const size_t total = (size_t)kNumBuckets * kHeadsStride * kListCap;
+    for (size_t i = gid; i < total; i += gsz) {
+        if (kcnt[i / kListCap] == 0) continue;
+        uint2 e = klist[i];
+        const uint32_t p = kentry_pos(e);
+        const uint32_t np = p > forward_len ? p - forward_len : 0u;
+        e.x = (e.x & 0xfe000000u) | np;
+        klist[i] = e;
+    }
+}
+
+} // namespace orz

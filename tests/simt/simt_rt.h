@@ -275,6 +275,10 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     return cudaSuccess;
 }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int *d) {
+    *d = 0;
+    return cudaSuccess;
+}
 cudaError_t cudaGetLastError();
 static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (simt::last_error() ? simt::last_error() : "emulated failure"); }
 static inline cudaError_t cudaMalloc(void **p, size_t n) {
