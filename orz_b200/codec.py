@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import LZCfg, OrzError, check, load
+from ._lib import ORZ_ENOSPC, LZCfg, OrzError, check, load
 
 LZ_BLOCK_SIZE = (1 << 25) - 1            # lib.rs:31
 LZ_CHUNK_SIZE = 1 << 20                  # lib.rs:32
@@ -63,18 +63,27 @@ def encode_batch(sources, cfg=2, device: int = 0):
 
 
 def decode_batch(targets, out_caps=None, device: int = 0):
+    """Independent streams.  Without explicit capacities the output buffers start at 16x the compressed size and grow 4x on
+    ORZ_ENOSPC (ROLZ streams of repetitive data exceed any fixed ratio; the reference writes to a growing Write)."""
     L = load()
     n = len(targets)
     ins = [_u8(t) for t in targets]
+    grow = out_caps is None
     caps = list(out_caps) if out_caps is not None else [max(1 << 16, a.size * 16) for a in ins]
-    outs = [np.empty(max(c, 1), dtype=np.uint8) for c in caps]
-    inp = (C.c_void_p * n)(*[a.ctypes.data if a.size else None for a in ins])
-    inl = (C.c_size_t * n)(*[a.size for a in ins])
-    outp = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
-    outc = (C.c_size_t * n)(*caps)
-    outl = (C.c_size_t * n)()
-    check(L.orz_decode_batch(device, n, inp, inl, outp, outc, outl), "decoding failed")
-    return [outs[i][: outl[i]].tobytes() for i in range(n)]
+    for _ in range(8):
+        outs = [np.empty(max(c, 1), dtype=np.uint8) for c in caps]
+        inp = (C.c_void_p * n)(*[a.ctypes.data if a.size else None for a in ins])
+        inl = (C.c_size_t * n)(*[a.size for a in ins])
+        outp = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        outc = (C.c_size_t * n)(*caps)
+        outl = (C.c_size_t * n)()
+        rc = L.orz_decode_batch(device, n, inp, inl, outp, outc, outl)
+        if rc == ORZ_ENOSPC and grow:
+            caps = [c * 4 for c in caps]
+            continue
+        check(rc, "decoding failed")
+        return [outs[i][: outl[i]].tobytes() for i in range(n)]
+    check(ORZ_ENOSPC, "decoding failed")
 
 
 def encode_segmented(source, segment_size: int = 1 << 24, cfg=2, device: int = 0) -> bytes:

@@ -162,7 +162,7 @@ struct EncStream {
     int32_t status;       // 0 running, 1 done, <0 error code
     uint32_t n_chunks;
     unsigned long long dbg[8]; // stage A counters: steps, executor spin iterations (own / lazy1 / lazy2 probe), builds, aborted builds
-    unsigned long long dbg7[8]; // v7 resolver cycles: total, load, walk, hand-over, repair, wait; repairs by cause
+    unsigned long long dbg7[16]; // v7: resolver cycles total, load, walk, hand-over, repair, wait; records repaired, rebuilt from HBM; builder cycles; list lag
 };
 
 // Per-stream decoder control block (lz.rs:348-357 LZDecoder, lib.rs:99-127 loop state)

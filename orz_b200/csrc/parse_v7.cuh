@@ -56,12 +56,13 @@ namespace orz {
 
 constexpr int kListCap = 64;           // entries per key list (circular, newest at (count-1) % 64)
 constexpr int kMaxDepth7 = 48;         // deepest LZCfg depth this kernel handles (levels 0-2 use 45)
-constexpr int kRing7 = 512;            // probe records kept in CTA 0's shared memory (positions)
-constexpr uint32_t kLead7 = kRing7 - 64; // builders stay this close to the parse position
+constexpr int kRing7 = 512;            // probe record slots in CTA 0's shared memory
 constexpr int kExtCand = 48;           // candidates per record kept for repairs
 constexpr int kSumWords = 12;          // summary words per record
 constexpr int kExtWords = 2 + kExtCand; // F_ext, ord0, candidates
 constexpr int kQueue7 = 512;           // step queue / recent-step log entries
+constexpr int kInRing = 4096;           // bytes of the window mirrored in CTA 0's shared memory
+constexpr uint32_t kInAhead = 1536;    // ... from 2048 bytes behind the parse position to this far ahead of it
 constexpr uint32_t kOrdMask = 0x7fffffffu;
 constexpr uint32_t kTyLit = 0, kTyWord = 1, kTyMatch = 2;
 
@@ -126,18 +127,22 @@ __device__ __forceinline__ uint32_t ldcg_u8(const uint8_t *p) {
 
 struct ParseShared7 {
     uint16_t words[32768];                  // lz.rs:52 — resolver only
-    uint32_t sum[kRing7][kSumWords];        // probe summaries, record of position y at y % 512
+    uint32_t sum[kRing7][kSumWords];        // probe summaries; position y lives in its builder's own slots: slot7<NBW>(y)
     uint32_t ext[kRing7][kExtWords];        // per record: F_ext, ord0, then lcp | expected << 8 | (ord0 - ord) << 16 per candidate
     uint4 queue[kQueue7];                   // decided steps: resolver -> committer; the tail doubles as the recent-step log
     uint32_t lastkey[4096];                 // position of the latest decided step whose key hashes here (0 = none in this launch)
     uint32_t bcnt[kNumBuckets];             // inserts into the bucket decided so far (ordinal of the next insert)
     uint32_t cnt[kNumCtx];                  // committer: items per rank-coder context in this chunk
+    uint32_t inring[kInRing / 4];           // window bytes around the parse position (byte p at p % 4096), kept by the feeder warp
+    uint32_t rc_pos[32], rc_exp[32], rc_ord[32]; // repair scratch: recent steps with the record's key
     uint32_t spos;                          // parse position (resolver -> builders)
     uint32_t fpos;                          // every step at a position < fpos is committed to HBM (committer -> builders)
     uint32_t qhead;                         // steps queued (resolver)
-    uint32_t qdone;                         // steps committed (committer)
+    uint32_t qdone;                         // steps whose list entries are committed (list committer)
+    uint32_t qitem;                         // steps whose items are written (item committer)
     uint32_t done;
-    uint32_t pad[3];
+    uint32_t fed_hi;                        // inring holds window bytes [max(fed_lo0, fed_hi - 4096), fed_hi)
+    uint32_t fed_lo0;
 };
 
 // summary words
@@ -220,7 +225,7 @@ struct Build7 {
 // insert count at the time y is decided.  Writes summary + ext through `sum`/`ext` (local or DSMEM pointers) and
 // publishes the stamp last.  Warp-cooperative.
 __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint32_t F, const volatile uint32_t *bcnt_src, uint32_t *sum,
-                                              uint32_t *ext, int lane) {
+                                              uint32_t *ext, uint32_t slot, int lane) {
     const uint8_t *win = B.win;
     const uint32_t prev4 = ld_u32_unaligned(win, y - 4); // bytes y-4 .. y-1
     const uint32_t cur4 = ld_u32_unaligned(win, y);      // bytes y .. y+3
@@ -314,7 +319,7 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
     const uint32_t ord0 = bcast0(kentry_ord(en));
     const int last = ncand - 1;
     const uint32_t lo0 = __shfl_sync(kFull, kentry_ord(en), last >= 0 ? (last & 31) : 0), lo1 = __shfl_sync(kFull, kentry_ord(en1), last >= 0 ? (last & 31) : 0);
-    const uint32_t ordmin = last < 0 ? 0u : (last < 32 ? lo0 : lo1);
+    const uint32_t ordmin = last < 0 ? kNone : (last < 32 ? lo0 : lo1); // kNone: no candidate
     // words updates of the two possible outcomes (lz.rs:208,233): words[hash2(s'-3)] = bytes s'-2, s'-1
     const uint32_t hw_lit = (b_m2 & 0x7fu) | ((b_m3 & 0x7fu) | is_alnum(b_m4) << 7) << 7; // s' = y+1
     const uint32_t wv_lit = b_m1 | (cur4 & 0xffu) << 8;
@@ -330,7 +335,7 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
     // ---- publish: ext (all lanes), summary words 1.. (lane 0), fence, stamp
     if (ok0) ext[2 + lane] = (uint32_t)lcp0 | kentry_exp(en) << 8 | ((ord0 - kentry_ord(en)) & 0xfffu) << 16;
     if (ok1 && 32 + lane < kExtCand) ext[2 + 32 + lane] = (uint32_t)lcp1 | kentry_exp(en1) << 8 | ((ord0 - kentry_ord(en1)) & 0xfffu) << 16;
-    uint32_t *gx = B.gext + (size_t)(y % kRing7) * kExtCand;
+    uint32_t *gx = B.gext + (size_t)slot * kExtCand;
     if (ok0) gx[lane] = p0;
     if (ok1 && 32 + lane < kExtCand) gx[32 + lane] = p1;
     if (lane == 0) {
@@ -352,17 +357,162 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
     if (lane == 0) st_release_u32(&sum[0], y);
 }
 
-// NW warps per CTA, K CTAs per stream (a thread-block cluster).  CTA 0: warp 0 resolver, warp 1 committer, the warps that
-// do not share the resolver's SM sub-partition build; CTAs 1..K-1: all warps build.
-template <int NW, int K>
-struct Dims7 {
-    static constexpr int NB0 = NW - 2 - (NW - 1) / 4 + ((NW - 1) / 4 > 0 ? 0 : 0); // builders in CTA 0: warps >= 2 with warp % 4 != 0
-    static constexpr int NBW = NB0 + (K - 1) * NW;
+// Window bytes for repairs: from the shared-memory ring where it is guaranteed stable (the feeder only moves when the parse
+// position does, and a repair holds it still), from HBM otherwise.
+struct ByteSrc7 {
+    const uint8_t *win;
+    const uint32_t *ring;
+    uint32_t lo, hi; // ring-safe byte range [lo, hi)
+    __device__ __forceinline__ uint32_t u32(uint32_t p) const {
+        if (p >= lo && p + 8 <= hi) {
+            const uint32_t w0 = ring[(p >> 2) & (kInRing / 4 - 1)], w1 = ring[((p >> 2) + 1) & (kInRing / 4 - 1)];
+            return __funnelshift_r(w0, w1, (p & 3u) * 8u);
+        }
+        return ld_u32_unaligned(win, p);
+    }
+    // mem.rs:41-51 restated byte-exact: longest common prefix of [a..) and [b..), capped at 240
+    __device__ __forceinline__ int lcp(uint32_t a, uint32_t b) const {
+        for (int i = 0; i < kMatchMax; i += 4) {
+            const uint32_t x = u32(a + i) ^ u32(b + i);
+            if (x) return i + ((__ffs(x) - 1) >> 3);
+        }
+        return kMatchMax;
+    }
 };
 
+// REPAIR without draining.  The record of y was built against the state below its frontier F_ext; since then steps with y's key
+// may have been decided (they sit in the step log, committed or not), and candidates may have left the ring.  The exact candidate
+// sequence at decision time T is  [steps in [F_ext, T) with y's key, newest first]  followed by  [the record's own candidates that
+// are still alive]; matcher.rs:135-228 is re-resolved over that sequence and the summary rewritten with frontier T.
+// Returns false if the record has to be rebuilt from HBM instead (incomplete record, log does not reach back to F_ext, > 32 recent steps).
+__device__ __forceinline__ bool repair_record7(ParseShared7 &shl, const Build7 &B, const ByteSrc7 &src, uint32_t y, uint32_t slot, uint32_t T,
+                                               uint32_t qhead, int lane) {
+    uint32_t *rs = shl.sum[slot];
+    const uint32_t *ex = shl.ext[slot];
+    const uint32_t w1 = rs[1];
+    if ((w1 >> 27) & 1u) return false;
+    const uint32_t key = w1 & 0x1fffffu, nold = (w1 >> 21) & 0x3fu, c = key >> 13;
+    const uint32_t F_ext = ex[0], ord0 = ex[1];
+    const uint32_t bc = shl.bcnt[c];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // ---- 1. steps with this key decided since the record's frontier, newest first
+    uint32_t k = 0;
+    bool reached = false;
+    for (int r = 0; r < 14 && !reached; r++) {
+        const int idx = (int)qhead - 1 - (r * 32 + lane);
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (idx >= 0) e = shl.queue[idx % kQueue7];
+        const uint32_t epos = e.x & 0x1ffffffu;
+        const bool inrange = idx >= 0 && epos >= F_ext;
+        const bool hit = inrange && (e.z & 0x1fffffu) == key;
+        const unsigned hm = __ballot_sync(kFull, hit);
+        const uint32_t slot = k + (uint32_t)__popc(hm & lt_mask);
+        if (hit && slot < 32u) {
+            shl.rc_pos[slot] = epos;
+            shl.rc_exp[slot] = e.z >> 21;
+            shl.rc_ord[slot] = e.y;
+        }
+        k += (uint32_t)__popc(hm);
+        if (__ballot_sync(kFull, !inrange)) reached = true;
+    }
+    if (!reached || k > 32u) return false;
+    __syncwarp();
+    // ---- 2. merged candidate sequence, 32 per round: lanes < k hold the recent steps (round 0), the others the record's candidates
+    int dmax = B.depth0 > B.depth1 ? B.depth0 : B.depth1;
+    dmax = dmax > B.depth2 ? dmax : B.depth2;
+    FmState st;
+    st.max_len = kMatchMin - 1;
+    st.exp_best = kMatchMin;
+    st.best = -1;
+    st.done = B.depth0 <= 0;
+    int m1 = -1, m2 = -1;
+    uint32_t best_ord = 0, best_exp = 0, last_ord = kNone;
+    uint32_t *gx = B.gext + (size_t)slot * kExtCand;
+    for (int round = 0; round < 2; round++) {
+        const int m = round * 32 + lane;
+        bool valid = false;
+        int lcp = -1;
+        uint32_t exp = 0, ord = 0, cpos = 0;
+        bool recent = false;
+        if (m < (int)k) {
+            recent = true;
+            cpos = shl.rc_pos[m];
+            exp = shl.rc_exp[m];
+            ord = shl.rc_ord[m];
+            valid = m < dmax;
+            if (valid) lcp = src.lcp(cpos, y);
+        } else {
+            const int j = m - (int)k;
+            if (j < (int)nold && m < dmax) {
+                const uint32_t w = ex[2 + j];
+                lcp = (int)(w & 0xffu);
+                exp = (w >> 8) & 0xffu;
+                ord = (ord0 - ((w >> 16) & 0xfffu)) & kOrdMask;
+                valid = ((bc - 1 - ord) & kOrdMask) <= (uint32_t)(kRing - 1); // still among the bucket's last 4094 inserts
+            }
+        }
+        const unsigned vm = __ballot_sync(kFull, valid);
+        const int nv = vm == 0xffffffffu ? 32 : (__ffs(~vm) - 1); // alive candidates form a prefix
+        valid = lane < nv;
+        m1 = max(m1, warp_max((valid && m < B.depth1) ? lcp : -1));
+        m2 = max(m2, warp_max((valid && m < B.depth2) ? lcp : -1));
+        const int before = st.best;
+        fm_round(st, valid && m < B.depth0, lcp, exp, m, lane, [&](int ml) {
+            const uint32_t p = recent ? cpos : ldcg_u32(&gx[m - (int)k]);
+            return src.u32(p + ml - 3) == src.u32(y + ml - 3);
+        });
+        if (st.best != before && st.best >= round * 32) {
+            best_ord = __shfl_sync(kFull, ord, st.best & 31);
+            best_exp = __shfl_sync(kFull, exp, st.best & 31);
+        }
+        if (nv > 0) last_ord = __shfl_sync(kFull, ord, nv - 1);
+        if (nv < 32) break;
+    }
+    uint32_t mlen = 0, wexp = 0, word = 0;
+    if (st.max_len >= kMatchMin && y + (uint32_t)st.max_len < B.sbuf_len && st.best >= 0) { // matcher.rs:183
+        mlen = (uint32_t)st.max_len;
+        word = best_ord;
+        wexp = best_exp;
+    }
+    uint32_t hw_m = 0, wv_m = 0;
+    if (mlen > 0) { // lz.rs:208: words[hash2(s'-3)] = bytes s'-2, s'-1 with s' = y + len
+        const uint32_t t4 = src.u32(y + mlen - 5), t2 = src.u32(y + mlen - 2);
+        const uint32_t x3 = (t4 >> 16) & 0xffu, x4 = (t4 >> 8) & 0xffu, x5 = t4 & 0xffu;
+        hw_m = (x3 & 0x7fu) | ((x4 & 0x7fu) | is_alnum(x5) << 7) << 7;
+        wv_m = t2 & 0xffffu;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t c1 = m1 < 0 ? 0u : (m1 > 255 ? 255u : (uint32_t)m1);
+        const uint32_t c2 = m2 < 0 ? 0u : (m2 > 255 ? 255u : (uint32_t)m2);
+        rs[3] = mlen | c1 << 8 | c2 << 16 | wexp << 24;
+        rs[4] = word;
+        rs[5] = last_ord;
+        rs[6] = T;
+        rs[8] = hw_m | wv_m << 15;
+    }
+    __syncwarp();
+    return true;
+}
+
+// Record slots are private to builders: builder b = y % NBW owns SL = 512 / NBW slots and is the only writer of the record of y,
+// (y % NBW) * SL + (y / NBW) % SL.  A builder handles its positions in increasing order, so a build that finishes late (the parse
+// already went past y) can only overwrite that builder's own, older record — never a newer record of another builder.
+template <int NBW>
+__device__ __forceinline__ uint32_t slot7(uint32_t y) {
+    constexpr uint32_t SL = (uint32_t)kRing7 / (uint32_t)NBW;
+    return (y % (uint32_t)NBW) * SL + (y / (uint32_t)NBW) % SL;
+}
+
+// NW warps per CTA, K CTAs per stream (a thread-block cluster).  CTA 0: warp 0 resolver, warp 1 committer, the warps that
+// do not share the resolver's SM sub-partition build; CTAs 1..K-1: all warps build.
 template <int NW, int K, bool STATS>
 __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams) {
     constexpr int NT = NW * 32;
+    static_assert(NW % 4 == 0 && NW >= 8, "stage A v7: warps per CTA");
+    constexpr int NB0 = NW - 4 - (NW / 4 - 1); // builders in CTA 0: warps >= 4 that do not share the resolver's SM sub-partition
+    constexpr int NBW = NB0 + (K - 1) * NW;    // builder warps of the cluster
+    constexpr uint32_t kLead = ((uint32_t)kRing7 / NBW) * NBW - 40u; // builders stay this close to the parse position
     EncStream *S = &streams[blockIdx.x / K];
     const unsigned rank = K > 1 ? cluster_cta_rank() : 0u;
     ORZ_DYN_SHARED(smem_raw);
@@ -382,7 +532,14 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
             shl.fpos = S->spos;
             shl.qhead = 0;
             shl.qdone = 0;
+            shl.qitem = 0;
             shl.done = 0;
+            // the feeder starts 2048 bytes behind the parse position (16-byte aligned, inside the allocated window)
+            uint32_t f0 = (S->spos - 2048u) & ~15u;
+            const uint32_t wlo = (S->win_lo + 15u) & ~15u;
+            if (S->win_lo > 0 && f0 < wlo) f0 = wlo;
+            shl.fed_lo0 = f0;
+            shl.fed_hi = f0;
         }
     }
     __syncthreads();
@@ -405,12 +562,14 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
             // ============================================================== resolver
             volatile uint32_t *v_qhead = &shl.qhead;
             volatile uint32_t *v_qdone = &shl.qdone;
+            volatile uint32_t *v_qitem = &shl.qitem;
             const uint32_t items_cap = S->items_cap < kChunkItems ? S->items_cap : kChunkItems;
             uint32_t spos = S->spos;
             uint32_t after_literal = S->after_literal;
             uint32_t n_items = 0, qhead = 0;
-            unsigned long long n_windows = 0, n_wait = 0, n_repair = 0, n_rep_conf = 0, n_rep_alive = 0, n_rep_inc = 0;
+            unsigned long long n_windows = 0, n_wait = 0, n_repair = 0, n_rep_rec = 0, n_rep_hard = 0;
             long long cyc_wait = 0, cyc_walk = 0, cyc_commit = 0, cyc_repair = 0, cyc_load = 0;
+            unsigned long long lag_steps = 0, lag_pos = 0;
             const long long t_begin = STATS ? clock64() : 0;
             const unsigned lt_mask = (1u << lane) - 1u;
             int wd_code = 0;
@@ -418,7 +577,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
             while (spos < sbuf_len && n_items < items_cap) {
                 const long long t0 = STATS ? clock64() : 0;
                 const uint32_t x = spos + (uint32_t)lane;
-                uint32_t *rs = shl.sum[x % kRing7];
+                uint32_t *rs = shl.sum[slot7<NBW>(x)];
                 // ---- load this lane's record
                 const uint32_t stamp = ld_acquire_u32(&rs[0]);
                 const bool ready = stamp == x;
@@ -457,7 +616,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 const uint32_t lk = shl.lastkey[kh];
                 // exactness of the record at decision time (see the header): no step with this key since F, oldest candidate alive
                 const bool confl = lk >= F;
-                const int room = ncand == 0 ? 64 : (int)(kRing - 1) - (int)((bc - 1 - ordmin) & kOrdMask);
+                const int room = ordmin == kNone ? 64 : (int)(kRing - 1) - (int)((bc - 1 - ordmin) & kOrdMask);
                 const bool st_bad = !ready || confl || incomplete || room < 0;
                 const bool tight = room < 32;
                 const uint32_t fl = (st_bad ? 1u : 0u) | (tight ? 2u : 0u) | (ready ? 4u : 0u);
@@ -537,7 +696,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 // ---- hand the decided steps to the committer and fold them into the shared tables
                 if (nsteps > 0) {
                     // queue space: the committer must have passed the entries about to be overwritten
-                    while ((int)(qhead + nsteps - bcast0(ld_vol_u32(v_qdone))) > kQueue7 - 8) ORZ_POLL();
+                    while ((int)(qhead + nsteps - bcast0(ld_vol_u32(v_qdone))) > kQueue7 - 8 || (int)(qhead + nsteps - bcast0(ld_vol_u32(v_qitem))) > kQueue7 - 8)
+                        ORZ_POLL();
                     const unsigned pm = __ballot_sync(kFull, onpath);
                     const bool writes = onpath && my_ty != kTyWord;
                     const uint32_t mywu = my_ty == kTyMatch ? wmat : wlit;
@@ -567,23 +727,52 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                         *v_qhead = qhead;
                         *v_spos = spos;
                     }
+                    if (STATS) {
+                        lag_steps += qhead - ld_vol_u32(v_qdone);
+                        lag_pos += spos - ld_vol_u32(&shl.fpos);
+                    }
                 }
                 const long long t3 = STATS ? clock64() : 0;
                 if (STATS) cyc_commit += t3 - t2;
                 if (stop == 1 && spos < sbuf_len && n_items < items_cap) {
-                    // ---- REPAIR: the record of spos (or of a lazy neighbour it needs) is stale.  Drain the committer and rebuild
-                    // the records of spos, spos+1, spos+2 against the now fully committed state; the next window sees them exact.
+                    // ---- REPAIR: the record of spos (or of a lazy neighbour it needs) is stale.  Re-resolve it in place from the step
+                    // log (repair_record7); a record that cannot be repaired that way is rebuilt from HBM after the committer drained.
                     if (STATS) n_repair++;
-                    while (bcast0(ld_vol_u32(v_qdone)) != qhead) ORZ_POLL();
-                    __threadfence();
+                    ByteSrc7 src;
+                    src.win = B.win;
+                    src.ring = shl.inring;
+                    const uint32_t flo = shl.fed_lo0, fhi = bcast0(ld_vol_u32(&shl.fed_hi));
+                    src.lo = spos - 2048u > flo ? spos - 2048u : flo;
+                    src.hi = fhi;
+                    bool lzneed0 = false;
                     for (uint32_t k = 0; k < 3; k++) {
                         const uint32_t y = spos + k;
                         if (y > last_pos) break;
                         // only records that are built and stale; a record that is not there yet is left to its builder
-                        uint32_t *ys = shl.sum[y % kRing7];
+                        const uint32_t yslot = slot7<NBW>(y);
+                        uint32_t *ys = shl.sum[yslot];
                         const uint32_t have_y = bcast0(ld_vol_u32(ys));
-                        if (have_y != y) continue;
-                        build_record7(B, y, spos, shl.bcnt, ys, shl.ext[y % kRing7], lane);
+                        bool stale = false;
+                        if (have_y == y) {
+                            const uint32_t yw1 = ys[1], ykey = yw1 & 0x1fffffu, yordmin = ys[5], yF = ys[6];
+                            const uint32_t ybc = shl.bcnt[ykey >> 13];
+                            const uint32_t ylk = shl.lastkey[(ykey ^ (ykey >> 9)) & 4095u];
+                            stale = ylk >= yF || ((yw1 >> 27) & 1u) || (yordmin != kNone && ((ybc - 1 - yordmin) & kOrdMask) > (uint32_t)(kRing - 1));
+                        }
+                        if (have_y == y && stale && (k == 0 || lzneed0)) {
+                            if (!repair_record7(shl, B, src, y, yslot, spos, qhead, lane)) {
+                                if (STATS) n_rep_hard++;
+                                while (bcast0(ld_vol_u32(v_qdone)) != qhead) ORZ_POLL();
+                                __threadfence();
+                                build_record7(B, y, spos, shl.bcnt, ys, shl.ext[yslot], yslot, lane);
+                            }
+                            if (STATS) n_rep_rec++;
+                        }
+                        __syncwarp();
+                        if (k == 0) {
+                            const uint32_t m0 = have_y == y ? (ys[3] & 0xffu) : 0u;
+                            lzneed0 = m0 > 0 && m0 < (uint32_t)(kMatchMax / 2);
+                        }
                     }
                     __syncwarp();
                     if (STATS) cyc_repair += clock64() - t3;
@@ -611,17 +800,19 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                     S->dbg7[3] += (unsigned long long)cyc_commit;
                     S->dbg7[4] += (unsigned long long)cyc_repair;
                     S->dbg7[5] += (unsigned long long)cyc_wait;
-                    S->dbg7[6] += n_rep_conf + n_rep_alive + n_rep_inc;
+                    S->dbg7[6] += n_rep_rec;
+                    S->dbg7[7] += n_rep_hard;
+                    S->dbg7[9] += lag_steps;
+                    S->dbg7[10] += lag_pos;
                 }
             }
         } else if (rank == 0 && warp == 1) {
-            // ============================================================== committer
+            // ============================================================== list committer: key-list appends, then the frontier.
+            // This is all the builders read, so the frontier trails the parse by one HBM round trip per 32 steps.
             volatile uint32_t *v_qhead = &shl.qhead;
             volatile uint32_t *v_qdone = &shl.qdone;
-            Item *items = S->items;
             uint2 *klist = S->klist;
             uint32_t *kcnt = S->kcnt;
-            uint8_t *lmarr = S->lm;
             uint32_t tail = 0;
             const unsigned lt_mask = (1u << lane) - 1u;
             for (;;) {
@@ -637,9 +828,56 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 const bool act = (uint32_t)lane < n;
                 uint4 rec = make_uint4(0, 0, 0, 0);
                 if (act) rec = shl.queue[(tail + (uint32_t)lane) % kQueue7];
-                const uint32_t pos = rec.x & 0x1ffffffu, ty = (rec.x >> 25) & 3u, al = (rec.x >> 27) & 1u;
+                const uint32_t pos = rec.x & 0x1ffffffu, ty = (rec.x >> 25) & 3u;
                 const uint32_t ord = rec.y, key = rec.z & 0x1fffffu, mlen = rec.z >> 21;
-                const uint32_t c = key >> 13, e = key & 0x1fffu;
+                const uint32_t kidx = (key >> 13) * kHeadsStride + (key & 0x1fffu);
+                uint32_t kc = 0;
+                if (act) kc = ldcg_u32(&kcnt[kidx]);
+                ORZ_COST(450);
+                // append in step order (matcher.rs:115-121: the new node becomes the head of its hash entry's chain)
+                const unsigned same_k = __match_any_sync(kFull, act ? kidx : (0x80000000u | (uint32_t)lane));
+                if (act) {
+                    const uint32_t rk = (uint32_t)__popc(same_k & lt_mask);
+                    klist[(size_t)kidx * kListCap + (kc + rk) % kListCap] = kentry_make(pos, ty == kTyMatch ? mlen : 0u, ord);
+                }
+                __threadfence();
+                __syncwarp();
+                if (act && !(same_k & ~lt_mask & ~(1u << lane))) kcnt[kidx] = kc + (uint32_t)__popc(same_k);
+                __threadfence();
+                __syncwarp();
+                tail += n;
+                const uint32_t lastpos = __shfl_sync(kFull, pos, (int)n - 1);
+                if (lane == 0) {
+                    st_release_u32(&shl.fpos, lastpos + 1);
+                    *v_qdone = tail;
+                }
+                __syncwarp();
+            }
+        } else if (rank == 0 && warp == 3) {
+            // ============================================================== item committer: lenmin bytes and items.  Nothing on
+            // the parse or build path reads what it writes (match_len_min only shapes the emitted length code), so it runs at
+            // its own pace behind the queue.
+            volatile uint32_t *v_qhead = &shl.qhead;
+            volatile uint32_t *v_qitem = &shl.qitem;
+            Item *items = S->items;
+            uint8_t *lmarr = S->lm;
+            uint32_t tail = 0;
+            const unsigned lt_mask = (1u << lane) - 1u;
+            for (;;) {
+                const uint32_t dn = bcast0(ld_vol_u32(v_done));
+                const uint32_t head = bcast0(ld_vol_u32(v_qhead));
+                if (head == tail) {
+                    if (dn) break;
+                    ORZ_POLL();
+                    continue;
+                }
+                const uint32_t n = head - tail < 32u ? head - tail : 32u;
+                const bool act = (uint32_t)lane < n;
+                uint4 rec = make_uint4(0, 0, 0, 0);
+                if (act) rec = shl.queue[(tail + (uint32_t)lane) % kQueue7];
+                const uint32_t ty = (rec.x >> 25) & 3u, al = (rec.x >> 27) & 1u;
+                const uint32_t ord = rec.y, key = rec.z & 0x1fffffu, mlen = rec.z >> 21;
+                const uint32_t c = key >> 13;
                 const uint32_t ro = rec.w & 0xfffu, wexp = (rec.w >> 12) & 0xffu, unl = (rec.w >> 20) & 0xffu, byte = rec.w & 0xffu;
                 const bool is_m = act && ty == kTyMatch;
                 // ring slots: the insert goes to (head + 1) % 4094 where head = slot of the previous insert (matcher.rs:63,77);
@@ -649,37 +887,43 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 const uint32_t mslot = (mord + 1) % kRing;
                 const uint32_t wkey_ins = act ? (c << 12 | slot) : (0x80000000u | (uint32_t)lane);
                 const uint32_t wkey_m = is_m ? (c << 12 | mslot) : (0x40000000u | (uint32_t)lane);
-                // lenmin of the matched node as stored; the serial pass below applies the effects of earlier steps of this batch
+                // lenmin of the matched node as stored; the pass below applies the effects of earlier steps of this batch
                 uint32_t cur_lm = 0;
                 if (is_m) cur_lm = ldcg_u8(&lmarr[c * kNodesStride + mslot]);
-                const uint32_t kidx = c * kHeadsStride + e;
-                uint32_t kc = 0;
-                if (act) kc = ldcg_u32(&kcnt[kidx]);
                 ORZ_COST(450);
-                // matcher.rs:62-80 in step order: [bump the matched node's lenmin] then [write the new node, lenmin 0]
+                // matcher.rs:62-80 in step order: [bump the matched node's lenmin] then [write the new node, lenmin 0].
+                // Only steps that can interact need the ordered pass: two steps matching the same node, or a step matching a node
+                // inserted by an earlier step of this batch (its reduced offset is then < 32).
+                const unsigned grp = __match_any_sync(kFull, wkey_m);
+                const unsigned involved = __ballot_sync(kFull, is_m && (ro < 32u || (grp & ~(1u << lane)) != 0u));
                 uint32_t new_lm = 0;     // value this lane's bump writes
                 bool bump = false;
                 bool ins_dead = false, bump_dead = false; // a later step of the batch overwrites the location
-                for (uint32_t i = 0; i < n; i++) {
+                const int last = involved ? 31 - __clz(involved) : -1; // effects only flow INTO involved steps: stop there
+                for (int i = 0; i <= last; i++) {
                     const uint32_t wm_i = __shfl_sync(kFull, wkey_m, i);
                     const uint32_t wi_i = __shfl_sync(kFull, wkey_ins, i);
                     uint32_t bv = 0xffffffffu;
-                    if ((uint32_t)lane == i && is_m && cur_lm <= mlen) {
+                    if (lane == i && is_m && cur_lm <= mlen) {
                         bump = true;
                         new_lm = mlen + 1 < 127u ? mlen + 1 : 127u;
                         bv = new_lm;
                     }
                     bv = __shfl_sync(kFull, bv, i);
-                    if ((uint32_t)lane > i) {
+                    if (lane > i) {
                         if (bv != 0xffffffffu && wkey_m == wm_i) cur_lm = bv; // an earlier step bumped the node this lane matched
                         if (wkey_m == wi_i) cur_lm = 0;                        // ... or it IS that step's new node
                     }
-                    if ((uint32_t)lane < i) { // later writes to the same byte make this lane's stores dead
+                    if (lane < i) { // later writes to the same byte make this lane's stores dead
                         if (wkey_ins == wi_i || (bv != 0xffffffffu && wkey_ins == wm_i)) ins_dead = true;
                         if (bump && (wkey_m == wi_i || (bv != 0xffffffffu && wkey_m == wm_i))) bump_dead = true;
                     }
-                    if ((uint32_t)lane == i && bump && wkey_m == wkey_ins) bump_dead = true; // matcher.rs:66-77: own insert overwrites it
                 }
+                if (is_m && lane > last && cur_lm <= mlen) { // no other step of the batch touches this node: plain matcher.rs:66-71
+                    bump = true;
+                    new_lm = mlen + 1 < 127u ? mlen + 1 : 127u;
+                }
+                if (bump && wkey_m == wkey_ins) bump_dead = true; // matcher.rs:66-77: the step's own insert overwrites the bumped slot
                 // ---- items (lz.rs:173-236)
                 const uint32_t ctx = c | al << 8;
                 const unsigned same_ctx = __match_any_sync(kFull, act ? ctx : (0x10000u | (uint32_t)lane));
@@ -720,33 +964,46 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                     if (bump && !bump_dead) lmarr[c * kNodesStride + mslot] = (uint8_t)new_lm;
                     if (!ins_dead) lmarr[c * kNodesStride + slot] = 0;
                 }
-                // ---- key lists: append in step order
-                const unsigned same_k = __match_any_sync(kFull, act ? kidx : (0x80000000u | (uint32_t)lane));
-                if (act) {
-                    const uint32_t rk = (uint32_t)__popc(same_k & lt_mask);
-                    klist[(size_t)kidx * kListCap + (kc + rk) % kListCap] = kentry_make(pos, ty == kTyMatch ? mlen : 0u, ord);
-                }
-                __threadfence();
-                __syncwarp();
-                if (act && !(same_k & ~lt_mask & ~(1u << lane))) kcnt[kidx] = kc + (uint32_t)__popc(same_k);
-                __threadfence();
+                __threadfence(); // the next batch's lenmin loads (other lanes, L2) must see these stores
                 __syncwarp();
                 tail += n;
-                const uint32_t lastpos = __shfl_sync(kFull, pos, (int)n - 1);
-                if (lane == 0) {
-                    st_release_u32(&shl.fpos, lastpos + 1);
-                    *v_qdone = tail;
-                }
+                if (lane == 0) *v_qitem = tail;
                 __syncwarp();
             }
-        } else if (rank != 0 || (warp >= 2 && (warp & 3) != 0)) {
+        } else if (rank == 0 && warp == 2) {
+            // ============================================================== feeder: window bytes around the parse position
+            volatile uint32_t *v_fed = &shl.fed_hi;
+            uint32_t fed = shl.fed_lo0;
+            const uint32_t top = S->win_hi & ~15u;
+            for (;;) {
+                if (bcast0(ld_vol_u32(v_done))) break;
+                const uint32_t sp = bcast0(ld_vol_u32(v_spos));
+                uint32_t target = (sp + kInAhead) & ~15u;
+                if (target > top) target = top;
+                if (fed >= target) {
+#ifdef ORZ_SIMT_EMU
+                    ORZ_POLL();
+#else
+                    __nanosleep(100);
+#endif
+                    continue;
+                }
+                while (fed < target) {
+                    const uint32_t p = fed + 16u * (uint32_t)lane;
+                    if (p < target) *reinterpret_cast<uint4 *>(&shl.inring[(p & (kInRing - 1)) >> 2]) = *reinterpret_cast<const uint4 *>(B.win + p);
+                    fed = fed + 512u < target ? fed + 512u : target;
+                }
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) *v_fed = fed;
+            }
+        } else if (rank != 0 || (warp >= 4 && (warp & 3) != 0)) {
             // ============================================================== builders
-            constexpr int NB0 = NW - 2 - (NW - 1) / 4;
-            constexpr int NBW = NB0 + (K - 1) * NW;
             int bi;
-            if (rank == 0) bi = warp - 2 - warp / 4;
+            if (rank == 0) bi = warp - 4 - warp / 4;
             else bi = NB0 + ((int)rank - 1) * NW + warp;
             unsigned long long nbuild = 0;
+            long long cyc_build = 0;
             const uint32_t last_pos = sbuf_len + 1;
             uint32_t y = S->spos;
             y += ((uint32_t)bi + (uint32_t)NBW - y % (uint32_t)NBW) % (uint32_t)NBW; // first position >= spos owned by this builder
@@ -754,7 +1011,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 if (bcast0(ld_vol_u32(v_done))) break;
                 const uint32_t sp = bcast0(ld_vol_u32(v_spos));
                 if (y < sp) y += ((sp - y + (uint32_t)NBW - 1) / (uint32_t)NBW) * (uint32_t)NBW; // the parse went past: skip
-                if (y > last_pos || y > sp + kLead7) {
+                if (y > last_pos || y > sp + kLead) {
 #ifdef ORZ_SIMT_EMU
                     ORZ_POLL();
 #else
@@ -764,11 +1021,19 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 }
                 const uint32_t F = bcast0(ld_acquire_u32(&sh.fpos));
                 if (lane == 0) V7_TRACE("B%d y %u F %u sp %u\n", bi, y, F, sp);
-                build_record7(B, y, F, sh.bcnt, sh.sum[y % kRing7], sh.ext[y % kRing7], lane);
-                if (STATS) nbuild++;
+                const uint32_t yslot = slot7<NBW>(y);
+                const long long tb = STATS ? clock64() : 0;
+                build_record7(B, y, F, sh.bcnt, sh.sum[yslot], sh.ext[yslot], yslot, lane);
+                if (STATS) {
+                    nbuild++;
+                    cyc_build += clock64() - tb;
+                }
                 y += (uint32_t)NBW;
             }
-            if (STATS && lane == 0) atomicAdd(&S->dbg[4], nbuild);
+            if (STATS && lane == 0) {
+                atomicAdd(&S->dbg[4], nbuild);
+                atomicAdd(&S->dbg7[8], (unsigned long long)cyc_build);
+            }
         }
     }
     __syncthreads();

@@ -33,6 +33,7 @@ def emu():
 
 def _run(emu, spec, env_extra=None, timeout=600):
     env = dict(os.environ, ORZ_B200_LIB=emu, ORZ_B200_TEST_EMULATOR="1", SIMT_SWITCH_LIMIT="20000000000")
+    env.setdefault("ORZ_B200_V7_CLUSTER", "1")  # one CTA per stream keeps the emulation short; cluster runs are explicit
     env.update(env_extra or {})
     out = subprocess.run([sys.executable, os.path.join(SIMT, "run_case.py"), json.dumps(spec)], env=env, capture_output=True,
                          text=True, timeout=timeout)
@@ -76,51 +77,33 @@ def test_emulated_kernels_under_random_interleavings(emu, seed):
     assert got == [_want(_data(case), 2)]
 
 
-def test_emulated_v3_variants(emu):
-    """v3 (single-thread executor, per-bucket seqlocks) is the many-stream default; force it for one stream too."""
+def test_emulated_legacy_v3_variants(emu):
+    """v3 (single-thread executor, per-bucket seqlocks; ring-record layout) is the many-stream kernel; pin it for one stream too."""
     case = {"gen": "text_like", "n": 20000, "seed": 31}
-    got = _run(emu, {"level": 2, "cases": [case]}, {"ORZ_B200_PARSE": "3", "ORZ_B200_PARSE_BUILDERS": "8"})
+    got = _run(emu, {"level": 2, "cases": [case]}, {"ORZ_B200_LEGACY_STAGE_A": "v3s"})
     assert got == [_want(_data(case), 2)]
-    got = _run(emu, {"level": 2, "cases": [case]}, {"ORZ_B200_PARSE": "3"})
+    got = _run(emu, {"level": 2, "cases": [case]}, {"ORZ_B200_LEGACY_STAGE_A": "v3"})
     assert got == [_want(_data(case), 2)]
 
 
-@pytest.mark.parametrize("parse", ["4:32", "4:8"])
-def test_emulated_parse_v4_matches_oracle(emu, parse):
-    """Stage A v4 (windowed warp resolver, lock-free builders; parse_v4.cuh) forced for a batch, 32/16/8-warp blocks."""
-    ver, _, warps = parse.partition(":")
-    env = {"ORZ_B200_PARSE": ver}
-    if warps:
-        env["ORZ_B200_PARSE_WARPS"] = warps
+def test_emulated_legacy_v4_matches_oracle(emu):
+    """Stage A v4 (windowed warp resolver, lock-free builders; parse_v4.cuh): the ring-record layout's one-stream kernel, used for
+    LZCfg depths beyond the key lists' 48 candidates."""
     cases = [{"gen": "text_like", "n": 30000, "seed": 51}, {"gen": "low_entropy", "n": 30000, "seed": 52}]
-    got = _run(emu, {"level": 2, "cases": cases, "batch": True}, env)
+    got = _run(emu, {"level": 2, "cases": cases, "batch": True}, {"ORZ_B200_LEGACY_STAGE_A": "v4"})
     assert got == [_want(_data(c), 2) for c in cases]
 
 
-@pytest.mark.parametrize("cluster,park,seed", [("1", "1", None), ("2", "1", None), ("4", "0", "3")])
-def test_emulated_parse_v5_cluster_builders(emu, cluster, park, seed):
-    """parse_v5.cuh: v4 with thread-block-cluster builders publishing over DSMEM, parked warps, sleeping idle builders
-    (the emulator runs the CTAs of a cluster together and maps CTA 0's shared memory for the others)."""
-    env = {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": cluster, "ORZ_B200_PARSE_PARK": park}
+@pytest.mark.parametrize("cluster,seed,n", [("1", None, 40000), ("1", "3", 20000), ("8", None, 6000)])
+def test_emulated_parse_v7(emu, cluster, seed, n):
+    """parse_v7.cuh, the default: key lists in HBM, builders publishing probe records into CTA 0's shared memory (over DSMEM when
+    the stream owns a cluster: the emulator runs the CTAs of a cluster together), decide-only resolver, committer warp."""
+    env = {"ORZ_B200_V7_CLUSTER": cluster}
     if seed:
         env["SIMT_SEED"] = seed
-    n = 12000 if cluster in ("1", "2") else 5000  # (4 CTAs = 4096 fibres: keep the emulation short)
     cases = [{"gen": "text_like", "n": n, "seed": 71}, {"gen": "low_entropy", "n": n, "seed": 72}]
     got = _run(emu, {"level": 2, "cases": cases, "batch": True}, env)
     assert got == [_want(_data(c), 2) for c in cases]
-
-
-@pytest.mark.parametrize("group,cluster,warps,seed", [("8", "1", "16", None), ("16", "1", "32", "4"), ("8", "2", "32", None)])
-def test_emulated_parse_v6_sub_warp_builders(emu, group, cluster, warps, seed):
-    """parse_v6.cuh: builder warps split into groups of 8 / 16 lanes, one probe per group (segment-wise chain walks,
-    full-mask width-G collectives); the emulator also checks that no collective sits under a group-dependent branch."""
-    env = {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": group, "ORZ_B200_PARSE_CLUSTER": cluster, "ORZ_B200_PARSE_WARPS": warps}
-    if seed:
-        env["SIMT_SEED"] = seed
-    cases = [{"gen": "text_like", "n": 20000, "seed": 81}, {"gen": "low_entropy", "n": 20000, "seed": 82}]
-    level = 0 if seed else 2
-    got = _run(emu, {"level": level, "cases": cases, "batch": True}, env)
-    assert got == [_want(_data(c), level) for c in cases]
 
 
 def test_emulator_flags_divergent_collectives(tmp_path):
@@ -149,12 +132,10 @@ int main() {
     assert out.returncode == 0 and "different source sites" in out.stdout
 
 
-@pytest.mark.parametrize("env", [{"ORZ_B200_PARSE": "3"}, {"ORZ_B200_PARSE": "4"}, {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "2"},
-                                 {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "16"},
-                                 {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "4", "ORZ_B200_PARSE_WARPS": "16", "SIMT_SEED": "6"}])
+@pytest.mark.parametrize("env", [{"ORZ_B200_LEGACY_STAGE_A": "v3"}, {"ORZ_B200_LEGACY_STAGE_A": "v4"}, {"ORZ_B200_V7_CLUSTER": "1"},
+                                 {"ORZ_B200_V7_CLUSTER": "1", "SIMT_SEED": "6"}])
 def test_emulated_long_chain_walks(emu, env):
-    """Chains far longer than one gather round / one 29-link snapshot (datagen.long_chains): multi-round walks in v3-v5,
-    segment-wise walks with snapshot source switches in v6."""
+    """Chains far longer than one gather round (datagen.long_chains): multi-round walks in v3/v4, two-round candidate lists in v7."""
     case = {"gen": "long_chains", "n": 30000, "seed": 4}
     got = _run(emu, {"level": 2, "cases": [case]}, env)
     assert got == [_want(_data(case), 2)]
@@ -163,13 +144,13 @@ def test_emulated_long_chain_walks(emu, env):
 def test_emulated_operator_interface(emu):
     """orz_lzenc_new/encode/forward (chunk mode, host-driven) through the emulated kernels."""
     case = {"gen": "text_like", "n": 25000, "seed": 54}
-    got = _run(emu, {"level": 2, "cases": [case], "operators": True})
+    got = _run(emu, {"level": 2, "cases": [case], "operators": True}, {"ORZ_B200_V7_CLUSTER": "1"})
     assert got == [_want(_data(case), 2)]
 
 
 def test_emulated_parse_v4_under_random_interleavings(emu):
     case = {"gen": "text_like", "n": 20000, "seed": 53}
-    got = _run(emu, {"level": 1, "cases": [case]}, {"ORZ_B200_PARSE": "4", "SIMT_SEED": "7"})
+    got = _run(emu, {"level": 1, "cases": [case]}, {"ORZ_B200_LEGACY_STAGE_A": "v4", "SIMT_SEED": "7"})
     assert got == [_want(_data(case), 1)]
 
 
@@ -184,16 +165,18 @@ def scale_model():
     return cli, os.path.join(SIMT, "orz_oracle_small")
 
 
-@pytest.mark.parametrize("parse,gen,level,seed", [("3", "text_like", 2, None), ("4", "text_like", 2, None),
-                                                  ("4", "low_entropy", 1, "5"), ("3", "low_entropy", 0, "6"),
-                                                  ("6", "text_like", 1, "8"), ("6", "long_chains", 2, None)])
+@pytest.mark.parametrize("parse,gen,level,seed", [("v3", "text_like", 2, None), ("v4", "text_like", 2, None),
+                                                  ("v4", "low_entropy", 1, "5"), ("v3", "low_entropy", 0, "6"),
+                                                  ("7", "text_like", 2, None), ("7", "text_like", 1, "8"), ("7", "long_chains", 2, None),
+                                                  ("7", "low_entropy", 0, None)])
 def test_scale_model_multi_block_streams(scale_model, tmp_path, parse, gen, level, seed):
     cli, oracle = scale_model
     data = getattr(datagen, gen)(150_000 if seed is None else 100_000, seed=61)  # (random scheduling is the slower mode)
     src, want, got = tmp_path / "in", tmp_path / "want.orz", tmp_path / "got.orz"
     src.write_bytes(data)
     subprocess.check_call([oracle, "encode", str(level), str(src), str(want)], stderr=subprocess.DEVNULL)
-    env = dict(os.environ, ORZ_B200_PARSE=parse, SIMT_SWITCH_LIMIT="60000000000")
+    env = dict(os.environ, SIMT_SWITCH_LIMIT="60000000000")
+    env.update({"ORZ_B200_V7_CLUSTER": "1"} if parse == "7" else {"ORZ_B200_LEGACY_STAGE_A": parse})
     if seed:
         env["SIMT_SEED"] = seed
     subprocess.run([cli, str(level), str(src), str(got)], env=env, check=True, timeout=900, stderr=subprocess.DEVNULL)
