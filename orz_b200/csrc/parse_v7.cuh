@@ -57,6 +57,7 @@ namespace orz {
 constexpr int kListCap = 64;           // entries per key list (circular, newest at (count-1) % 64)
 constexpr int kMaxDepth7 = 48;         // deepest LZCfg depth this kernel handles (levels 0-2 use 45)
 constexpr int kRing7 = 512;            // probe record slots in CTA 0's shared memory
+constexpr uint32_t kLeadTarget7 = 192; // how far ahead of the parse records are built: every position of lead is a chance to go stale
 constexpr int kExtCand = 48;           // candidates per record kept for repairs
 constexpr int kSumWords = 12;          // summary words per record
 constexpr int kExtWords = 2 + kExtCand; // F_ext, ord0, candidates
@@ -236,7 +237,7 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
     const uint32_t e0 = hash_dword(cur4) % kHashSize;                                  // matcher.rs:136
     const uint32_t kidx = c * kHeadsStride + e0;
     const uint32_t gc = bcast0(ld_vol_u32(&bcnt_src[c]));
-    const uint32_t cnt = bcast0(ldcg_u32(&B.kcnt[kidx]));
+    const uint32_t cnt = bcast0(ldcg_u32(&B.kcnt[kidx + (F >> 31)])); // (F < 2^25: the term is 0; it only makes the load wait for F)
     const uint32_t avail = cnt < (uint32_t)kListCap ? cnt : (uint32_t)kListCap;
     int dmax = B.depth0 > B.depth1 ? B.depth0 : B.depth1;
     dmax = dmax > B.depth2 ? dmax : B.depth2;
@@ -352,7 +353,7 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
         sum[7] = hw_lit | wv_lit << 15;
         sum[8] = hw_m | wv_m << 15;
     }
-    __threadfence();
+    // the barrier orders every lane's stores before lane 0's release store of the stamp (cumulative: no fence per lane)
     __syncwarp();
     if (lane == 0) st_release_u32(&sum[0], y);
 }
@@ -512,7 +513,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
     static_assert(NW % 4 == 0 && NW >= 8, "stage A v7: warps per CTA");
     constexpr int NB0 = NW - 4 - (NW / 4 - 1); // builders in CTA 0: warps >= 4 that do not share the resolver's SM sub-partition
     constexpr int NBW = NB0 + (K - 1) * NW;    // builder warps of the cluster
-    constexpr uint32_t kLead = ((uint32_t)kRing7 / NBW) * NBW - 40u; // builders stay this close to the parse position
+    constexpr uint32_t kLeadMax = ((uint32_t)kRing7 / NBW) * NBW - 40u;
+    constexpr uint32_t kLead = kLeadMax < kLeadTarget7 ? kLeadMax : kLeadTarget7; // builders stay this close to the parse position
     EncStream *S = &streams[blockIdx.x / K];
     const unsigned rank = K > 1 ? cluster_cta_rank() : 0u;
     ORZ_DYN_SHARED(smem_raw);
@@ -567,36 +569,115 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
             uint32_t spos = S->spos;
             uint32_t after_literal = S->after_literal;
             uint32_t n_items = 0, qhead = 0;
-            unsigned long long n_windows = 0, n_wait = 0, n_repair = 0, n_rep_rec = 0, n_rep_hard = 0;
+            unsigned long long n_windows = 0, n_wait = 0, n_repair = 0, n_rep_rec = 0, n_rep_hard = 0, n_cut = 0;
             long long cyc_wait = 0, cyc_walk = 0, cyc_commit = 0, cyc_repair = 0, cyc_load = 0;
             unsigned long long lag_steps = 0, lag_pos = 0;
             const long long t_begin = STATS ? clock64() : 0;
             const unsigned lt_mask = (1u << lane) - 1u;
             int wd_code = 0;
             unsigned idle = 0;
+            uint32_t qlimit = (uint32_t)kQueue7 - 8u; // queue entries below this index are free (consumers re-read when it is reached)
             while (spos < sbuf_len && n_items < items_cap) {
                 const long long t0 = STATS ? clock64() : 0;
                 const uint32_t x = spos + (uint32_t)lane;
-                uint32_t *rs = shl.sum[slot7<NBW>(x)];
-                // ---- load this lane's record
-                const uint32_t stamp = ld_acquire_u32(&rs[0]);
-                const bool ready = stamp == x;
-                const uint4 a = *reinterpret_cast<const uint4 *>(&rs[0]);
-                const uint4 b = *reinterpret_cast<const uint4 *>(&rs[4]);
-                const uint32_t wmat = rs[8];
-                const unsigned rdy = __ballot_sync(kFull, ready);
-                if (lane == 0) V7_TRACE("R spos %u rdy %08x stamp %u\n", spos, rdy, stamp);
-                // a decision at lane l needs the records of l, l+1 and l+2
+                const uint32_t *rs = shl.sum[slot7<NBW>(x)];
+                // ---- load this lane's record.  The stamp is the builder's last store (release); the first 16 bytes are read in
+                // one shared-memory transaction, the rest afterwards, so a matching stamp covers every field.
+                const uint4 a = lds_volatile_v4(rs);
+                const uint4 b = lds_volatile_v4(rs + 4);
+                const uint32_t wmat = ld_vol_u32(rs + 8);
+                const bool ready = a.x == x;
                 const uint32_t last_pos = sbuf_len + 1; // the last position that has a record
-                unsigned need0 = 0x7u;
-                if (spos + 1 > last_pos) need0 = 0x1u;
-                else if (spos + 2 > last_pos) need0 = 0x3u;
-                if ((rdy & need0) != need0) { // the next step's records are not there yet
+                const uint32_t key = a.y & 0x1fffffu, c = key >> 13;
+                const bool incomplete = (a.y >> 27) & 1u;
+                const uint32_t h2 = a.z & 0x7fffu, b2 = a.z >> 15;
+                const uint32_t mlen = a.w & 0xffu, wexp = a.w >> 24;
+                const uint32_t word = b.x, ordmin = b.y, F = b.z, wlit = b.w;
+                const uint32_t lwe = shl.words[h2];                            // lz.rs:132
+                const uint32_t bc = shl.bcnt[c];
+                const uint32_t kh = (key ^ (key >> 9)) & 4095u;
+                const uint32_t lk = shl.lastkey[kh];
+                // exactness of the record at decision time (see the header): no step with this key since F, oldest candidate alive.
+                // `tight`: fewer than 32 further inserts keep the oldest candidate alive — exact only for the window's first step.
+                const int room = ordmin == kNone ? 64 : (int)(kRing - 1) - (int)((bc - 1 - ordmin) & kOrdMask);
+                const bool stale = ready && (lk >= F || incomplete || room < 0);
+                const bool tight = ready && room < 32;
+                const bool bad = stale || (lane > 0 && tight);
+                // neighbours: lane+1 supplies the depth1 lazy maximum, lane+2 the depth2 one (lz.rs:154-169)
+                const uint32_t nb = ((a.w >> 8) & 0xffffu) | ((stale || (lane > 2 && tight)) ? 1u : 0u) << 16 | (ready ? 0u : 1u) << 17;
+                const uint32_t nb1 = __shfl_down_sync(kFull, nb, 1), nb2 = __shfl_down_sync(kFull, nb, 2);
+                const uint32_t key1 = __shfl_down_sync(kFull, key, 1), key2 = __shfl_down_sync(kFull, key, 2);
+                const uint32_t lzn1 = nb1 & 0xffu, lzn2 = (nb2 >> 8) & 0xffu;
+                const bool lzneed = mlen > 0 && mlen < (uint32_t)(kMatchMax / 2);
+                const bool has1 = lane < 31 && x + 1 <= last_pos, has2 = lane < 30 && x + 2 <= last_pos;
+                // the step this lane takes IF it is on the path and nothing decided in this window before it interferes
+                const uint32_t lwm = lwe == b2 ? 1u : 0u;                       // lz.rs:133
+                const uint32_t ro0 = (bc - 1 - word) & kOrdMask;                // reduced offset with no further insert before it (matcher.rs:185)
+                const uint32_t rb = ro0 < 510u ? 1u : 0u;                       // robitlen < 8  <=>  reduced offset < 510
+                const bool rbsens = mlen > 0 && rb && ro0 + 31u >= 510u;        // an insert of this window could flip robitlen < 8
+                uint32_t pk = decide7(mlen, lzn1, lzn2, lwm, rb, x + 1 < sbuf_len);
+                const uint32_t ty = pk >> 8;
+                // type 3 ends the window at this lane: advance field 1 = a record must be repaired first, 2 = a record is not built yet
+                const bool nr = !ready || (has1 && ((nb1 >> 17) & 1u)) || (has2 && ((nb2 >> 17) & 1u));
+                const bool rep = bad || (lzneed && ((has1 && ((nb1 >> 16) & 1u)) || (has2 && ((nb2 >> 16) & 1u))));
+                if (nr) pk = 2u | 3u << 8;
+                else if (rep) pk = 1u | 3u << 8;
+                else if (lane >= 30 && x + 2 <= last_pos) pk = 3u | 3u << 8; // needs lanes beyond the window: next window
+                const uint32_t wu = ty == kTyWord ? 0xffffffffu : (ty == kTyMatch ? wmat : wlit); // lz.rs:208,233
+                const long long t1 = STATS ? clock64() : 0;
+                if (STATS) cyc_load += t1 - t0;
+
+                // ---- chase the step chain through the window (lz.rs:131-236): one shuffle per step, nothing else on the chain
+                uint32_t path = 0, cur = 0;
+                int stop = 0;
+                const uint32_t max_steps = items_cap - n_items;
+                for (;;) {
+                    const uint32_t v = __shfl_sync(kFull, pk, cur);
+                    if ((v >> 8) == 3u) {
+                        stop = (int)(v & 0xffu);
+                        break;
+                    }
+                    path |= 1u << cur;
+                    cur += v & 0xffu;
+                    if (cur >= 32 || spos + cur >= sbuf_len || (uint32_t)__popc(path) >= max_steps) break;
+                }
+                // ---- verify: a step is exact only if no EARLIER step of this window touched what it read — its own or its lazy
+                // neighbours' candidate lists (same key), its bucket's insert count when that flips robitlen < 8, its words entry.
+                // The path is cut at the first step that fails; it becomes the first step of the next window.
+                if (path & (path - 1)) { // two or more steps
+                    bool viol = false;
+                    uint32_t rest = path;
+                    while (rest) {
+                        const int j = __ffs(rest) - 1;
+                        rest &= rest - 1;
+                        const uint32_t kj = __shfl_sync(kFull, key, j);
+                        const uint32_t wj = __shfl_sync(kFull, wu, j);
+                        if (lane > j) {
+                            viol |= kj == key || (lzneed && (kj == key1 || kj == key2)) || (rbsens && (kj >> 13) == c) ||
+                                    (wj != 0xffffffffu && (wj & 0x7fffu) == h2);
+                        }
+                    }
+                    const unsigned vm = __ballot_sync(kFull, viol) & path;
+                    if (vm) {
+                        const int v = __ffs(vm) - 1;
+                        path &= (1u << v) - 1u;
+                        cur = (uint32_t)v;
+                        stop = 0;
+                        if (STATS) n_cut++;
+                    }
+                }
+                const uint32_t nsteps = (uint32_t)__popc(path);
+                const long long t2 = STATS ? clock64() : 0;
+                if (STATS) {
+                    cyc_walk += t2 - t1;
+                    n_windows++;
+                }
+                if (nsteps == 0 && stop == 2) { // the next step's records are not there yet
                     if (STATS) {
                         n_wait++;
                         cyc_wait += clock64() - t0;
                     }
-                    if (++idle > 200000000u) {
+                    if (++idle > 400000000u) {
                         wd_code = 1;
                         break;
                     }
@@ -604,124 +685,43 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                     continue;
                 }
                 idle = 0;
-                const uint32_t key = a.y & 0x1fffffu, c = key >> 13;
-                const uint32_t ncand = (a.y >> 21) & 0x3fu;
-                const bool incomplete = (a.y >> 27) & 1u;
-                const uint32_t h2 = a.z & 0x7fffu, b2 = a.z >> 15;
-                const uint32_t mlen = a.w & 0xffu, lz1 = (a.w >> 8) & 0xffu, lz2 = (a.w >> 16) & 0xffu, wexp = a.w >> 24;
-                const uint32_t word = b.x, ordmin = b.y, F = b.z, wlit = b.w;
-                uint32_t lwe = shl.words[h2];                                  // lz.rs:132 (kept current below)
-                const uint32_t bc = shl.bcnt[c];
-                const uint32_t kh = (key ^ (key >> 9)) & 4095u;
-                const uint32_t lk = shl.lastkey[kh];
-                // exactness of the record at decision time (see the header): no step with this key since F, oldest candidate alive
-                const bool confl = lk >= F;
-                const int room = ordmin == kNone ? 64 : (int)(kRing - 1) - (int)((bc - 1 - ordmin) & kOrdMask);
-                const bool st_bad = !ready || confl || incomplete || room < 0;
-                const bool tight = room < 32;
-                const uint32_t fl = (st_bad ? 1u : 0u) | (tight ? 2u : 0u) | (ready ? 4u : 0u);
-                const uint32_t fl1 = __shfl_down_sync(kFull, fl, 1), fl2 = __shfl_down_sync(kFull, fl, 2);
-                const uint32_t key1 = __shfl_down_sync(kFull, key, 1), key2 = __shfl_down_sync(kFull, key, 2);
-                const uint32_t lzn1 = __shfl_down_sync(kFull, lz1, 1), lzn2 = __shfl_down_sync(kFull, lz2, 2);
-                bool ownstale = st_bad || (lane > 0 && tight);
-                bool n1stale = lane >= 31 || (fl1 & 1u) || (lane > 0 && (fl1 & 2u));
-                bool n2stale = lane >= 30 || (fl2 & 1u) || (lane > 0 && (fl2 & 2u));
-                // records that are simply not built yet end the window instead of asking for a repair
-                const bool notready = !ready || (lane < 31 && !(fl1 & 4u) && x + 1 <= last_pos) || (lane < 30 && !(fl2 & 4u) && x + 2 <= last_pos);
-                const bool can_word = x + 1 < sbuf_len;
-                const bool lzneed = mlen > 0 && mlen < (uint32_t)(kMatchMax / 2);
-                // the four possible outcomes, indexed by last_word_matched * 2 + (robitlen < 8)
-                uint32_t nd = 0, nt = 0;
-#pragma unroll
-                for (uint32_t s = 0; s < 4; s++) {
-                    const uint32_t d = decide7(mlen, lzn1, lzn2, s >> 1, s & 1u, can_word);
-                    nd |= (d & 0xffu) << (8 * s);
-                    nt |= (d >> 8) << (2 * s);
-                }
-                const uint32_t ro0 = (bc - 1 - word) & kOrdMask; // reduced offset if no further insert precedes this step (matcher.rs:185)
-                uint32_t pend = 0;
-                // what this lane decided when its turn came
-                uint32_t my_ty = 0, my_d = 0, my_pend = 0, my_al = 0, my_lwe = 0;
-                bool onpath = false;
-                uint32_t cur = 0, nsteps = 0;
-                int stop = 0; // 1: repair needed at cur, 2: record not ready at cur
-                const long long t1 = STATS ? clock64() : 0;
-                if (STATS) cyc_load += t1 - t0;
 
-                // ---- walk the step chain through the window (lz.rs:131-236): one shuffle round per step
-                for (;;) {
-                    const uint32_t lwm = (lwe == b2) ? 1u : 0u;                        // lz.rs:133
-                    const uint32_t rb = (ro0 + pend < 510u) ? 1u : 0u;                 // robitlen < 8  <=>  reduced offset < 510
-                    const uint32_t sel = lwm * 2 + rb;
-                    const uint32_t d = (nd >> (8 * sel)) & 0xffu, ty = (nt >> (2 * sel)) & 3u;
-                    const uint32_t slow = notready ? 2u : ((ownstale || (lzneed && (n1stale || n2stale))) ? 1u : 0u);
-                    // type 3 = the window ends here: advance field 1 = repair needed, 2 = a record is not built yet
-                    const uint32_t pk = slow ? (slow | 3u << 8) : (d | ty << 8 | key << 10);   // key: 21 bits
-                    const uint32_t wu = ty == kTyWord ? 0xffffffffu : (ty == kTyMatch ? wmat : wlit);
-                    const uint32_t pk_s = __shfl_sync(kFull, pk, cur);
-                    const uint32_t wu_s = __shfl_sync(kFull, wu, cur);
-                    const uint32_t d_s = pk_s & 0xffu, ty_s = (pk_s >> 8) & 3u, key_s = pk_s >> 10;
-                    if (ty_s == 3u) {
-                        stop = (int)d_s;
-                        break;
-                    }
-                    if ((uint32_t)lane == cur) {
-                        onpath = true;
-                        my_ty = ty;
-                        my_d = d;
-                        my_pend = pend;
-                        my_al = after_literal;
-                        my_lwe = lwe;
-                    }
-                    nsteps++;
-                    after_literal = ty_s == kTyLit ? 1u : 0u;
-                    // keep every later lane's inputs current
-                    if ((uint32_t)lane > cur) {
-                        if ((key_s >> 13) == c) pend++;
-                        if (key_s == key) ownstale = true;
-                        if (key_s == key1) n1stale = true;
-                        if (key_s == key2) n2stale = true;
-                        if (wu_s != 0xffffffffu && (wu_s & 0x7fffu) == h2) lwe = wu_s >> 15;
-                    }
-                    cur += d_s;
-                    if (cur >= 30 || n_items + nsteps >= items_cap || spos + cur >= sbuf_len) break;
-                }
-                if (lane == 0) V7_TRACE("  walk nsteps %u cur %u stop %d mlen %u lz %u %u key %x F %u room %d fl %x\n", nsteps, cur, stop, mlen, lzn1, lzn2, key, F, room, fl);
-                const long long t2 = STATS ? clock64() : 0;
-                if (STATS) {
-                    cyc_walk += t2 - t1;
-                    n_windows++;
-                }
-
-                // ---- hand the decided steps to the committer and fold them into the shared tables
+                // ---- hand the decided steps to the committers and fold them into the shared tables
                 if (nsteps > 0) {
-                    // queue space: the committer must have passed the entries about to be overwritten
-                    while ((int)(qhead + nsteps - bcast0(ld_vol_u32(v_qdone))) > kQueue7 - 8 || (int)(qhead + nsteps - bcast0(ld_vol_u32(v_qitem))) > kQueue7 - 8)
-                        ORZ_POLL();
-                    const unsigned pm = __ballot_sync(kFull, onpath);
-                    const bool writes = onpath && my_ty != kTyWord;
-                    const uint32_t mywu = my_ty == kTyMatch ? wmat : wlit;
+                    const bool onpath = (path >> lane) & 1u;
+                    if (qhead + nsteps > qlimit) { // queue space: both committers must have passed the entries about to be overwritten
+                        for (;;) {
+                            const uint32_t d1 = bcast0(ld_vol_u32(v_qdone)), d2 = bcast0(ld_vol_u32(v_qitem));
+                            qlimit = (d1 < d2 ? d1 : d2) + (uint32_t)kQueue7 - 8u;
+                            if (qhead + nsteps <= qlimit) break;
+                            ORZ_POLL();
+                        }
+                    }
+                    // after_literal of a step = the step before it on the path was a literal (lz.rs:229)
+                    const unsigned below = path & lt_mask;
+                    const uint32_t pty = __shfl_sync(kFull, ty, below ? 31 - __clz(below) : 0);
+                    const uint32_t my_al = below ? (pty == kTyLit ? 1u : 0u) : after_literal;
+                    // ordinal of the step's insert: inserts of this window into the same bucket before it count
+                    const unsigned same_c = __match_any_sync(kFull, onpath ? c : (0x10000u | (uint32_t)lane));
+                    const uint32_t my_pend = (uint32_t)__popc(same_c & lt_mask);
+                    const bool writes = onpath && ty != kTyWord;
+                    const unsigned same_w = __match_any_sync(kFull, writes ? (wu & 0x7fffu) : (0x10000u | (uint32_t)lane));
                     if (onpath) {
-                        const uint32_t qi = qhead + (uint32_t)__popc(pm & lt_mask);
-                        const uint32_t ord = (bc + my_pend) & kOrdMask;
+                        const uint32_t qi = qhead + (uint32_t)__popc(below);
                         uint4 rec;
-                        rec.x = x | my_ty << 25 | my_al << 27;
-                        rec.y = ord;
-                        rec.z = key | (my_ty == kTyMatch ? mlen : 0u) << 21;
-                        rec.w = my_ty == kTyMatch ? (((ro0 + my_pend) & 0xfffu) | wexp << 12 | (my_lwe & 0xffu) << 20)
-                                                  : ((b2 & 0xffu) | (my_lwe & 0xffu) << 20);
+                        rec.x = x | ty << 25 | my_al << 27;
+                        rec.y = (bc + my_pend) & kOrdMask;
+                        rec.z = key | (ty == kTyMatch ? mlen : 0u) << 21;
+                        rec.w = ty == kTyMatch ? (((ro0 + my_pend) & 0xfffu) | wexp << 12 | (lwe & 0xffu) << 20) : ((b2 & 0xffu) | (lwe & 0xffu) << 20);
                         shl.queue[qi % kQueue7] = rec;
-                        atomicAdd(&shl.bcnt[c], 1u);
+                        if (!(same_c >> lane >> 1)) shl.bcnt[c] = bc + my_pend + 1; // the bucket's last step of the window
                         atomicMax(&shl.lastkey[kh], x);
+                        if (writes && !(same_w >> lane >> 1)) shl.words[wu & 0x7fffu] = (uint16_t)(wu >> 15); // the last writer of an index wins
                     }
-                    { // lz.rs:208,233 — the last writer of an index wins
-                        const unsigned same = __match_any_sync(kFull, writes ? (mywu & 0x7fffu) : (0x10000u | (uint32_t)lane));
-                        if (writes && (same >> lane) <= 1u) shl.words[mywu & 0x7fffu] = (uint16_t)(mywu >> 15);
-                    }
+                    after_literal = __shfl_sync(kFull, ty, 31 - __clz(path)) == kTyLit ? 1u : 0u;
                     qhead += nsteps;
                     n_items += nsteps;
                     spos += cur;
-                    __threadfence_block();
                     __syncwarp();
                     if (lane == 0) {
                         *v_qhead = qhead;
@@ -804,6 +804,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                     S->dbg7[7] += n_rep_hard;
                     S->dbg7[9] += lag_steps;
                     S->dbg7[10] += lag_pos;
+                    S->dbg7[11] += n_cut;
                 }
             }
         } else if (rank == 0 && warp == 1) {
@@ -1019,7 +1020,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
 #endif
                     continue;
                 }
-                const uint32_t F = bcast0(ld_acquire_u32(&sh.fpos));
+                // The list loads (L2, ld.cg) must be issued after the frontier was read: their address depends on it.
+                const uint32_t F = bcast0(ld_vol_u32(&sh.fpos));
                 if (lane == 0) V7_TRACE("B%d y %u F %u sp %u\n", bi, y, F, sp);
                 const uint32_t yslot = slot7<NBW>(y);
                 const long long tb = STATS ? clock64() : 0;
