@@ -57,7 +57,7 @@ namespace orz {
 constexpr int kListCap = 64;           // entries per key list (circular, newest at (count-1) % 64)
 constexpr int kMaxDepth7 = 48;         // deepest LZCfg depth this kernel handles (levels 0-2 use 45)
 constexpr int kRing7 = 512;            // probe record slots in CTA 0's shared memory
-constexpr uint32_t kLeadTarget7 = 192; // how far ahead of the parse records are built: every position of lead is a chance to go stale
+constexpr uint32_t kLeadTarget7 = 128; // how far ahead of the parse records are built: every position of lead is a chance to go stale
 constexpr int kExtCand = 48;           // candidates per record kept for repairs
 constexpr int kSumWords = 12;          // summary words per record
 constexpr int kExtWords = 2 + kExtCand; // F_ext, ord0, candidates
@@ -136,6 +136,8 @@ struct ParseShared7 {
     uint32_t cnt[kNumCtx];                  // committer: items per rank-coder context in this chunk
     uint32_t inring[kInRing / 4];           // window bytes around the parse position (byte p at p % 4096), kept by the feeder warp
     uint32_t rc_pos[32], rc_exp[32], rc_ord[32]; // repair scratch: recent steps with the record's key
+    uint32_t sbk[64], sbw[64];              // resolver scoreboards: lowest lane of the window that posted this key / words index
+    uint32_t lcnt[kNumBuckets], icnt[kNumBuckets]; // the committers' own insert counts (they number the inserts of a batch in order)
     uint32_t spos;                          // parse position (resolver -> builders)
     uint32_t fpos;                          // every step at a position < fpos is committed to HBM (committer -> builders)
     uint32_t qhead;                         // steps queued (resolver)
@@ -397,7 +399,7 @@ __device__ __forceinline__ bool repair_record7(ParseShared7 &shl, const Build7 &
     const uint32_t bc = shl.bcnt[c];
     const unsigned lt_mask = (1u << lane) - 1u;
     // ---- 1. steps with this key decided since the record's frontier, newest first
-    uint32_t k = 0;
+    uint32_t k = 0, newer_c = 0; // newer_c: steps of bucket c seen so far (all newer than the entry being looked at)
     bool reached = false;
     for (int r = 0; r < 14 && !reached; r++) {
         const int idx = (int)qhead - 1 - (r * 32 + lane);
@@ -407,13 +409,15 @@ __device__ __forceinline__ bool repair_record7(ParseShared7 &shl, const Build7 &
         const bool inrange = idx >= 0 && epos >= F_ext;
         const bool hit = inrange && (e.z & 0x1fffffu) == key;
         const unsigned hm = __ballot_sync(kFull, hit);
+        const unsigned cm = __ballot_sync(kFull, idx >= 0 && ((e.z >> 13) & 0xffu) == c);
         const uint32_t slot = k + (uint32_t)__popc(hm & lt_mask);
         if (hit && slot < 32u) {
             shl.rc_pos[slot] = epos;
             shl.rc_exp[slot] = e.z >> 21;
-            shl.rc_ord[slot] = e.y;
+            shl.rc_ord[slot] = (bc - 1 - (newer_c + (uint32_t)__popc(cm & lt_mask))) & kOrdMask; // its insert's ordinal in the bucket
         }
         k += (uint32_t)__popc(hm);
+        newer_c += (uint32_t)__popc(cm);
         if (__ballot_sync(kFull, !inrange)) reached = true;
     }
     if (!reached || k > 32u) return false;
@@ -525,7 +529,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
 
     if (active && rank == 0) {
         for (int i = tid; i < kNumCtx; i += NT) shl.cnt[i] = 0;
-        for (int i = tid; i < kNumBuckets; i += NT) shl.bcnt[i] = S->bcnt[i];
+        for (int i = tid; i < kNumBuckets; i += NT) shl.bcnt[i] = shl.lcnt[i] = shl.icnt[i] = S->bcnt[i];
+        for (int i = tid; i < 64; i += NT) shl.sbk[i] = shl.sbw[i] = 0xffffffffu;
         for (int i = tid; i < 4096; i += NT) shl.lastkey[i] = 0;
         for (int i = tid; i < kRing7; i += NT) shl.sum[i][0] = kNone;
         for (int i = tid; i < 32768 / 8; i += NT) reinterpret_cast<uint4 *>(shl.words)[i] = reinterpret_cast<const uint4 *>(S->words)[i];
@@ -602,9 +607,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 const int room = ordmin == kNone ? 64 : (int)(kRing - 1) - (int)((bc - 1 - ordmin) & kOrdMask);
                 const bool stale = ready && (lk >= F || incomplete || room < 0);
                 const bool tight = ready && room < 32;
-                const bool bad = stale || (lane > 0 && tight);
                 // neighbours: lane+1 supplies the depth1 lazy maximum, lane+2 the depth2 one (lz.rs:154-169)
-                const uint32_t nb = ((a.w >> 8) & 0xffffu) | ((stale || (lane > 2 && tight)) ? 1u : 0u) << 16 | (ready ? 0u : 1u) << 17;
+                const uint32_t nb = ((a.w >> 8) & 0xffffu) | (stale ? 1u : 0u) << 16 | (ready ? 0u : 1u) << 17 | (tight ? 1u : 0u) << 18;
                 const uint32_t nb1 = __shfl_down_sync(kFull, nb, 1), nb2 = __shfl_down_sync(kFull, nb, 2);
                 const uint32_t key1 = __shfl_down_sync(kFull, key, 1), key2 = __shfl_down_sync(kFull, key, 2);
                 const uint32_t lzn1 = nb1 & 0xffu, lzn2 = (nb2 >> 8) & 0xffu;
@@ -615,14 +619,19 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 const uint32_t ro0 = (bc - 1 - word) & kOrdMask;                // reduced offset with no further insert before it (matcher.rs:185)
                 const uint32_t rb = ro0 < 510u ? 1u : 0u;                       // robitlen < 8  <=>  reduced offset < 510
                 const bool rbsens = mlen > 0 && rb && ro0 + 31u >= 510u;        // an insert of this window could flip robitlen < 8
-                uint32_t pk = decide7(mlen, lzn1, lzn2, lwm, rb, x + 1 < sbuf_len);
-                const uint32_t ty = pk >> 8;
-                // type 3 ends the window at this lane: advance field 1 = a record must be repaired first, 2 = a record is not built yet
+                const uint32_t dec = decide7(mlen, lzn1, lzn2, lwm, rb, x + 1 < sbuf_len);
+                const uint32_t ty = dec >> 8, adv = dec & 0xffu;
+                // what the chase sees: advance (clamped to the window's end) | type << 8; type 3 ends the window at this lane:
+                // code 1 = a record must be repaired first, 2 = a record is not built yet, 3 = plain window boundary
                 const bool nr = !ready || (has1 && ((nb1 >> 17) & 1u)) || (has2 && ((nb2 >> 17) & 1u));
-                const bool rep = bad || (lzneed && ((has1 && ((nb1 >> 16) & 1u)) || (has2 && ((nb2 >> 16) & 1u))));
+                const bool rep = stale || (lzneed && ((has1 && ((nb1 >> 16) & 1u)) || (has2 && ((nb2 >> 16) & 1u))));
+                // a record whose oldest candidate is within 32 inserts of leaving the ring, or whose robitlen < 8 an insert could
+                // flip, is exact only for the window's FIRST step: later lanes end the window there
+                const bool edge = lane > 0 && (tight || rbsens || (lzneed && ((has1 && ((nb1 >> 18) & 1u)) || (has2 && ((nb2 >> 18) & 1u)))));
+                uint32_t pk = (adv + (uint32_t)lane > 32u ? 32u - (uint32_t)lane : adv) | ty << 8;
                 if (nr) pk = 2u | 3u << 8;
                 else if (rep) pk = 1u | 3u << 8;
-                else if (lane >= 30 && x + 2 <= last_pos) pk = 3u | 3u << 8; // needs lanes beyond the window: next window
+                else if (edge || (lane >= 30 && x + 2 <= last_pos) || x >= sbuf_len) pk = 3u | 3u << 8;
                 const uint32_t wu = ty == kTyWord ? 0xffffffffu : (ty == kTyMatch ? wmat : wlit); // lz.rs:208,233
                 const long long t1 = STATS ? clock64() : 0;
                 if (STATS) cyc_load += t1 - t0;
@@ -630,34 +639,46 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 // ---- chase the step chain through the window (lz.rs:131-236): one shuffle per step, nothing else on the chain
                 uint32_t path = 0, cur = 0;
                 int stop = 0;
-                const uint32_t max_steps = items_cap - n_items;
                 for (;;) {
                     const uint32_t v = __shfl_sync(kFull, pk, cur);
-                    if ((v >> 8) == 3u) {
+                    if (v >= 0x300u) {
                         stop = (int)(v & 0xffu);
                         break;
                     }
                     path |= 1u << cur;
                     cur += v & 0xffu;
-                    if (cur >= 32 || spos + cur >= sbuf_len || (uint32_t)__popc(path) >= max_steps) break;
+                    if (cur & 32u) break;
+                }
+                // the chunk's item limit (lz.rs:131): keep only the steps that still fit
+                const uint32_t max_steps = items_cap - n_items;
+                if ((uint32_t)__popc(path) > max_steps) {
+                    uint32_t keep = path;
+                    for (uint32_t i = (uint32_t)__popc(path); i > max_steps; i--) keep &= ~(1u << (31 - __clz(keep)));
+                    cur = (uint32_t)(__ffs(path & ~keep) - 1); // the first step that no longer fits
+                    path = keep;
+                    stop = 0;
                 }
                 // ---- verify: a step is exact only if no EARLIER step of this window touched what it read — its own or its lazy
-                // neighbours' candidate lists (same key), its bucket's insert count when that flips robitlen < 8, its words entry.
-                // The path is cut at the first step that fails; it becomes the first step of the next window.
+                // neighbours' candidate lists (same key) or its words entry — and no two steps write the same words entry.  Every step
+                // posts its key and its words index in two 64-entry scoreboards (the lowest lane wins); a step that finds an earlier
+                // lane under one of its own indices ends the window and becomes the first step of the next one.  Scoreboard
+                // aliases only cut windows short, they never change a decision.
+                const bool onp = (path >> lane) & 1u;
                 if (path & (path - 1)) { // two or more steps
-                    bool viol = false;
-                    uint32_t rest = path;
-                    while (rest) {
-                        const int j = __ffs(rest) - 1;
-                        rest &= rest - 1;
-                        const uint32_t kj = __shfl_sync(kFull, key, j);
-                        const uint32_t wj = __shfl_sync(kFull, wu, j);
-                        if (lane > j) {
-                            viol |= kj == key || (lzneed && (kj == key1 || kj == key2)) || (rbsens && (kj >> 13) == c) ||
-                                    (wj != 0xffffffffu && (wj & 0x7fffu) == h2);
-                        }
+                    const uint32_t sk = kh & 63u, sw = wu & 63u, sr = h2 & 63u;
+                    if (onp) {
+                        atomicMin(&shl.sbk[sk], (uint32_t)lane);
+                        if (wu != 0xffffffffu) atomicMin(&shl.sbw[sw], (uint32_t)lane);
                     }
+                    __syncwarp();
+                    const uint32_t k1h = (key1 ^ (key1 >> 9)) & 63u, k2h = (key2 ^ (key2 >> 9)) & 63u;
+                    bool viol = shl.sbk[sk] < (uint32_t)lane || shl.sbw[sr] < (uint32_t)lane || (wu != 0xffffffffu && shl.sbw[sw] < (uint32_t)lane);
+                    if (lzneed) viol = viol || shl.sbk[k1h] < (uint32_t)lane || shl.sbk[k2h] < (uint32_t)lane;
                     const unsigned vm = __ballot_sync(kFull, viol) & path;
+                    if (onp) { // leave the scoreboards clean
+                        shl.sbk[sk] = 0xffffffffu;
+                        if (wu != 0xffffffffu) shl.sbw[sw] = 0xffffffffu;
+                    }
                     if (vm) {
                         const int v = __ffs(vm) - 1;
                         path &= (1u << v) - 1u;
@@ -699,26 +720,25 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                     }
                     // after_literal of a step = the step before it on the path was a literal (lz.rs:229)
                     const unsigned below = path & lt_mask;
-                    const uint32_t pty = __shfl_sync(kFull, ty, below ? 31 - __clz(below) : 0);
+                    const int lastl = 31 - __clz(path);
+                    const uint32_t pty = __shfl_sync(kFull, ty, below ? 31 - __clz(below) : lastl);
                     const uint32_t my_al = below ? (pty == kTyLit ? 1u : 0u) : after_literal;
-                    // ordinal of the step's insert: inserts of this window into the same bucket before it count
-                    const unsigned same_c = __match_any_sync(kFull, onpath ? c : (0x10000u | (uint32_t)lane));
-                    const uint32_t my_pend = (uint32_t)__popc(same_c & lt_mask);
-                    const bool writes = onpath && ty != kTyWord;
-                    const unsigned same_w = __match_any_sync(kFull, writes ? (wu & 0x7fffu) : (0x10000u | (uint32_t)lane));
                     if (onpath) {
                         const uint32_t qi = qhead + (uint32_t)__popc(below);
                         uint4 rec;
                         rec.x = x | ty << 25 | my_al << 27;
-                        rec.y = (bc + my_pend) & kOrdMask;
+                        rec.y = word;                                   // ordinal of the matched node; the committers number the inserts
                         rec.z = key | (ty == kTyMatch ? mlen : 0u) << 21;
-                        rec.w = ty == kTyMatch ? (((ro0 + my_pend) & 0xfffu) | wexp << 12 | (lwe & 0xffu) << 20) : ((b2 & 0xffu) | (lwe & 0xffu) << 20);
+                        rec.w = wexp | (lwe & 0xffu) << 8 | (b2 & 0xffu) << 16;
                         shl.queue[qi % kQueue7] = rec;
-                        if (!(same_c >> lane >> 1)) shl.bcnt[c] = bc + my_pend + 1; // the bucket's last step of the window
+                        atomicAdd(&shl.bcnt[c], 1u);
                         atomicMax(&shl.lastkey[kh], x);
-                        if (writes && !(same_w >> lane >> 1)) shl.words[wu & 0x7fffu] = (uint16_t)(wu >> 15); // the last writer of an index wins
+                        if (ty != kTyWord) shl.words[wu & 0x7fffu] = (uint16_t)(wu >> 15); // (no two steps of a window share an index)
                     }
-                    after_literal = __shfl_sync(kFull, ty, 31 - __clz(path)) == kTyLit ? 1u : 0u;
+                    after_literal = __shfl_sync(kFull, ty, lastl) == kTyLit ? 1u : 0u;
+                    // the true advance of the last step (its chase value was clamped to the window)
+                    const uint32_t ladv = __shfl_sync(kFull, adv, lastl);
+                    if (!stop && (cur & 32u)) cur = (uint32_t)lastl + ladv;
                     qhead += nsteps;
                     n_items += nsteps;
                     spos += cur;
@@ -830,11 +850,17 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 uint4 rec = make_uint4(0, 0, 0, 0);
                 if (act) rec = shl.queue[(tail + (uint32_t)lane) % kQueue7];
                 const uint32_t pos = rec.x & 0x1ffffffu, ty = (rec.x >> 25) & 3u;
-                const uint32_t ord = rec.y, key = rec.z & 0x1fffffu, mlen = rec.z >> 21;
-                const uint32_t kidx = (key >> 13) * kHeadsStride + (key & 0x1fffu);
+                const uint32_t key = rec.z & 0x1fffffu, mlen = rec.z >> 21, c = key >> 13;
+                const uint32_t kidx = c * kHeadsStride + (key & 0x1fffu);
                 uint32_t kc = 0;
                 if (act) kc = ldcg_u32(&kcnt[kidx]);
                 ORZ_COST(450);
+                // the bucket's insert ordinal of every step (matcher.rs:63: the ring head advances by one per update)
+                const unsigned same_c = __match_any_sync(kFull, act ? c : (0x10000u | (uint32_t)lane));
+                const uint32_t cb = act ? shl.lcnt[c] : 0u;
+                __syncwarp();
+                const uint32_t ord = (cb + (uint32_t)__popc(same_c & lt_mask)) & kOrdMask;
+                if (act && !(same_c >> lane >> 1)) shl.lcnt[c] = cb + (uint32_t)__popc(same_c);
                 // append in step order (matcher.rs:115-121: the new node becomes the head of its hash entry's chain)
                 const unsigned same_k = __match_any_sync(kFull, act ? kidx : (0x80000000u | (uint32_t)lane));
                 if (act) {
@@ -877,9 +903,15 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 uint4 rec = make_uint4(0, 0, 0, 0);
                 if (act) rec = shl.queue[(tail + (uint32_t)lane) % kQueue7];
                 const uint32_t ty = (rec.x >> 25) & 3u, al = (rec.x >> 27) & 1u;
-                const uint32_t ord = rec.y, key = rec.z & 0x1fffffu, mlen = rec.z >> 21;
+                const uint32_t word = rec.y, key = rec.z & 0x1fffffu, mlen = rec.z >> 21;
                 const uint32_t c = key >> 13;
-                const uint32_t ro = rec.w & 0xfffu, wexp = (rec.w >> 12) & 0xffu, unl = (rec.w >> 20) & 0xffu, byte = rec.w & 0xffu;
+                const uint32_t wexp = rec.w & 0xffu, unl = (rec.w >> 8) & 0xffu, byte = (rec.w >> 16) & 0xffu;
+                const unsigned same_c = __match_any_sync(kFull, act ? c : (0x10000u | (uint32_t)lane));
+                const uint32_t cb = act ? shl.icnt[c] : 0u;
+                __syncwarp();
+                const uint32_t ord = (cb + (uint32_t)__popc(same_c & lt_mask)) & kOrdMask;
+                if (act && !(same_c >> lane >> 1)) shl.icnt[c] = cb + (uint32_t)__popc(same_c);
+                const uint32_t ro = (ord - 1 - word) & 0xfffu; // reduced offset (matcher.rs:185): inserts since the matched node
                 const bool is_m = act && ty == kTyMatch;
                 // ring slots: the insert goes to (head + 1) % 4094 where head = slot of the previous insert (matcher.rs:63,77);
                 // bucket insert number `ord` (0-based) therefore lands in slot (ord + 1) % 4094
