@@ -11,8 +11,11 @@ per rank, followed by one NCCL all-gather of the compressed spans; scaling is "w
 A step = one pass of the hot path over the whole input.
   value : input resident in HBM, timed with CUDA events on the library's stream (state reset + all kernels).
   e2e   : the public C-ABI call orz_encode_stream() with pinned HOST buffers (allocation, H2D, kernels, D2H inside).
-  roofline : the dominant kernel (orz_parse_kernel), algorithmic bytes (input read + stream written) over
-             its summed CUDA-event launch time, against the measured HBM peak in MEASURED_PEAKS.json.
+  roofline : the dominant kernel (stage A: orz_parse7_kernel for up to 8 streams per GPU), algorithmic bytes (input read + stream
+             written) over its summed CUDA-event launch time, against the measured HBM peak in MEASURED_PEAKS.json.
+  decode   : (N = 1) sub-record: the oracle-compressed corpus decoded on the GPU (BASELINE configs[4]), bit-identical flag.
+  segments : sub-record measured in the same run: enwik8 x 8 as 16 MiB segments (BASELINE configs[2]/[3] shape), strong scaling over
+             the N ranks, spans gathered with one variable-length collective; a sample segment is compared with the oracle.
   cpu_baseline : the C oracle (a port of the reference; no Rust toolchain exists here) on this box's host cores.
 --impl reference times that oracle as the reference arm (the real Rust build cannot run on the GPU box).
 """
@@ -106,105 +109,6 @@ def oracle_encode_threads(data_list, level):
     for t in ts:
         t.join()
     return time.perf_counter() - t0, outs
-
-
-VARIANTS = [
-    {"ORZ_B200_PARSE": "3"},
-    {"ORZ_B200_PARSE": "4", "ORZ_B200_PARSE_WARPS": "16"},
-    {"ORZ_B200_PARSE": "4", "ORZ_B200_PARSE_WARPS": "32"},
-    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "1", "ORZ_B200_PARSE_PARK": "1", "ORZ_B200_PARSE_WARPS": "32"},
-    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "1", "ORZ_B200_PARSE_PARK": "0", "ORZ_B200_PARSE_WARPS": "32"},
-    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "1", "ORZ_B200_PARSE_PARK": "1", "ORZ_B200_PARSE_WARPS": "16"},
-    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "1", "ORZ_B200_PARSE_PARK": "0", "ORZ_B200_PARSE_WARPS": "16"},
-    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "2", "ORZ_B200_PARSE_PARK": "1"},
-    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "4", "ORZ_B200_PARSE_PARK": "1"},
-    {"ORZ_B200_PARSE": "5", "ORZ_B200_PARSE_CLUSTER": "8", "ORZ_B200_PARSE_PARK": "1"},
-    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "32"},
-    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "16"},
-    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "16", "ORZ_B200_PARSE_WARPS": "32"},
-    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "16", "ORZ_B200_PARSE_WARPS": "16"},
-    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "4", "ORZ_B200_PARSE_WARPS": "16"},
-    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_CLUSTER": "4"},
-    {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_CLUSTER": "8"},
-]
-
-
-MULTI_VARIANTS = [  # many independent streams (the segment-parallel extension): (bytes per stream, streams, switches)
-    (1 << 20, 48, {"ORZ_B200_PARSE": "3"}),
-    (1 << 20, 48, {"ORZ_B200_PARSE": "4", "ORZ_B200_PARSE_WARPS": "16"}),
-    (1 << 20, 48, {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "16"}),
-    (1 << 18, 192, {"ORZ_B200_PARSE": "3"}),
-    (1 << 18, 192, {"ORZ_B200_PARSE": "3", "ORZ_B200_DBG": "64"}),
-    (1 << 18, 192, {"ORZ_B200_PARSE": "4", "ORZ_B200_PARSE_WARPS": "8"}),
-    (1 << 18, 192, {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "8", "ORZ_B200_PARSE_WARPS": "8"}),
-    (1 << 18, 192, {"ORZ_B200_PARSE": "6", "ORZ_B200_PARSE_GROUP": "4", "ORZ_B200_PARSE_WARPS": "8"}),
-]
-
-
-def _probe(nb, ns, env, timeout, device=0):
-    """One variant in its own process (tools/variant_probe.py): a faulting or hanging kernel cannot take the bench down."""
-    try:
-        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "variant_probe.py"), str(nb), str(ns)] +
-                           [f"{k}={v}" for k, v in env.items()], capture_output=True, text=True, timeout=timeout,
-                           env=dict(os.environ, ORZ_PROBE_DEVICE=str(device)))
-        line = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else ""
-        if p.returncode == 0 and line.startswith("{"):
-            return json.loads(line)
-        return {"env": env, "streams": ns, "error": (p.stderr.strip().splitlines() or ["rc %d" % p.returncode])[-1][:200]}
-    except subprocess.TimeoutExpired:
-        return {"env": env, "streams": ns, "error": "timeout"}
-    except Exception as e:  # noqa: BLE001
-        return {"env": env, "streams": ns, "error": repr(e)[:200]}
-
-
-def probe_variants(nbytes=6_000_000, timeout=120, multi=True, done=None):
-    """Side measurement, NOT the metric: every stage A variant in the tree (v3, v4, the opt-in v5 / v6 families) on the first
-    6 MB of the corpus as one stream, and a few of them on batches of independent streams, one subprocess each.  `done`:
-    results autotune_stage_a already has (not measured twice)."""
-    done = done or []
-    res = list(done)
-    seen = [r.get("env") for r in done if r.get("bytes") == nbytes]
-    jobs = [(nbytes, 1, env) for env in VARIANTS if env not in seen] + (MULTI_VARIANTS if multi else [])
-    for nb, ns, env in jobs:
-        res.append(_probe(nb, ns, env, timeout))
-    return {"note": "side measurement, -l2, stage A kernel time (CUDA events): one stream = the first 6 MB of the corpus; "
-                    "batches = consecutive slices; identical_to_v3 compares with stage A v3's streams; not the metric",
-            "results": res}
-
-
-def autotune_stage_a(nbytes=6_000_000, confirm_bytes=18_000_000, timeout=120, device=0):
-    """Pick the stage A kernel for the one-stream workload on THIS GPU.  Every variant of VARIANTS encodes the first 6 MB
-    of the corpus (two chunks) in its own process; those whose stream
-    equals stage A v3's are candidates; the fastest wins if it beats the library default by more than 5 %; the winner
-    must then reproduce v3's stream on the first 18 MB (a block slide and `forward`).  Returns (switches, results);
-    switches == {} keeps the library default.  bench.py compares the whole-corpus stream of whatever it times with the
-    oracle's in any case."""
-    results = []
-    base = None
-    best_env, best = {}, 0.0
-    for env in VARIANTS:
-        r = _probe(nbytes, 1, env, timeout, device)
-        results.append(r)
-        v = r.get("mb_s") if r.get("identical_to_v3") else None
-        if v is None:
-            continue
-        if env == DEFAULT_VARIANT:
-            base = v
-        if int(env.get("ORZ_B200_PARSE_CLUSTER", "1")) > 1:
-            v /= 1.10  # a thread-block cluster (K SMs for one stream) must win by 10 % more than a single-CTA kernel
-        if v > best:
-            best_env, best = env, v
-    if not best_env or (base is not None and best <= base * 1.05):
-        return {}, results
-    conf = _probe(confirm_bytes, 1, best_env, timeout * 2, device)
-    conf["role"] = "confirmation of the selected variant over a block slide"
-    results.append(conf)
-    if not conf.get("identical_to_v3"):
-        return {}, results
-    return dict(best_env), results
-
-
-DEFAULT_VARIANT = {"ORZ_B200_PARSE": "4", "ORZ_B200_PARSE_WARPS": "16"}  # what launch_parse picks for one stream
 
 
 def main():
@@ -354,35 +258,8 @@ def main():
         odist.gather_spans(spans, device)
         torch.cuda.synchronize()
 
-    # ---- stage A autotune (exact one-stream workload only; ORZ_BENCH_TUNE=0 or an explicit ORZ_B200_PARSE disables it)
-    tuned, tune_results = {}, []
-    tune_state = "off"
-    if (not decode_dir and args.workload == "exact" and os.environ.get("ORZ_BENCH_TUNE", "1") != "0"
-            and "ORZ_B200_PARSE" not in os.environ):
-        tune_state = "default kept"
-        try:
-            if rank == 0:
-                tuned, tune_results = autotune_stage_a(device=dev)
-            if world > 1:
-                box = [tuned]
-                dist.broadcast_object_list(box, src=0)
-                tuned = box[0]
-        except Exception as e:  # noqa: BLE001
-            tuned, tune_state = {}, "autotune failed: " + repr(e)[:120]
-        if tuned:
-            os.environ.update(tuned)
-            tune_state = "autotuned on the first 6 MB of the corpus, confirmed on 18 MB against stage A v3"
-    tune_check = None  # the tuned kernel's whole-corpus stream is compared with the oracle's after the first warm-up pass
-
-    def drop_tuning(why):
-        nonlocal tuned, tune_state
-        for k in tuned:
-            os.environ.pop(k, None)
-        tuned, tune_state = {}, "default kept: " + why
-
     def measure():
         """W warm-up + K timed passes (resident and end-to-end); returns the per-step lists and the clock sample."""
-        nonlocal tune_check
         dev_ms, parse_ms, emit_ms, parse_launches, launches = [], [], [], [], []
         wall = []
         e2e_s = []
@@ -394,22 +271,7 @@ def main():
                 sampler = ClockSampler(dev) if rank == 0 else None
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            if tuned and it == 0:
-                # first pass with the tuned kernel: it must complete and reproduce the oracle's stream, else back to the default
-                try:
-                    batch.run()
-                    if tune_check is None:
-                        from oracle import pyoracle
-                        pyoracle.build()
-                        tune_check = pyoracle.encode(streams[0], LEVEL)
-                    if batch.download(0) != tune_check:
-                        drop_tuning("the tuned kernel's stream differed from the oracle's")
-                        batch.run()
-                except Exception as e:  # noqa: BLE001
-                    drop_tuning("the tuned kernel failed: " + repr(e)[:80])
-                    batch.run()
-            else:
-                batch.run()
+            batch.run()
             gather_spans()
             t1 = time.perf_counter()
             if it >= args.warmup:
@@ -440,15 +302,6 @@ def main():
         return dev_ms, parse_ms, emit_ms, parse_launches, launches, wall, e2e_s, clocks
 
     dev_ms, parse_ms, emit_ms, parse_launches, launches, wall, e2e_s, clocks = measure()
-    if tuned and tune_check is not None:
-        # the tuned kernel was checked on its first pass; its LAST (timed) pass must be the oracle's stream too, and both paths
-        # (resident and host-buffer) must agree — otherwise the measurement is repeated with the library default
-        host = pin_out[0].a if hasattr(pin_out[0], "a") else pin_out[0].numpy()  # (.a: the torch stand-in of the CPU flow test)
-        if batch.download(0) != tune_check or host[: int(outl[0])].tobytes() != tune_check:
-            drop_tuning("a later pass of the tuned kernel differed from the oracle's stream; re-measured")
-            dev_ms, parse_ms, emit_ms, parse_launches, launches, wall, e2e_s, clocks = measure()
-
-
     comp_bytes = sum(batch.result_len(i) for i in range(n))
     # cross-check e2e output against the resident run
     assert sum(int(outl[i]) for i in range(n)) == comp_bytes
@@ -466,6 +319,32 @@ def main():
         ts = torch.tensor([plain_bytes, total_in, comp_bytes], dtype=torch.float64, device=f"cuda:{dev}")
         dist.all_reduce(ts, op=dist.ReduceOp.SUM)
         plain_all, in_all, out_all = (int(x) for x in ts.tolist())
+    # ------------------------------------------------------------------ bit-identity of what was just timed (every rank checks its own stream)
+    identical = None
+    if args.workload == "exact":
+        from oracle import pyoracle
+        pyoracle.build()
+        sample = raw_streams[0] if decode_dir else streams[0]
+        t0 = time.perf_counter()
+        want = pyoracle.decode(streams[0], int(np.asarray(sample).size) + 64) if decode_dir else pyoracle.encode(sample, LEVEL)
+        cpu_s = time.perf_counter() - t0
+        host = pin_out[0].a if hasattr(pin_out[0], "a") else pin_out[0].numpy()  # (.a: the torch stand-in of the CPU flow test)
+        identical = batch.download(0) == want and host[: int(outl[0])].tobytes() == want  # resident path AND host-buffer path
+        if world > 1:
+            ok = torch.tensor([1 if identical else 0], dtype=torch.int32, device=f"cuda:{dev}")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            identical = bool(int(ok[0]))
+    batch.close()
+    del flush
+
+    # ------------------------------------------------------------------ sub-record: independent 16 MiB segments sharded over the ranks
+    seg_rec = None
+    if not decode_dir and args.workload == "exact" and args.bytes == N_BYTES and not os.environ.get("ORZ_BENCH_NO_SEGMENTS"):
+        seg_rec = segments_subrecord(torch, dist if world > 1 else None, rank, world, dev, np.asarray(data))
+    # ------------------------------------------------------------------ sub-record: decode (BASELINE configs[4]), one GPU
+    dec_rec = None
+    if rank == 0 and world == 1 and not decode_dir and args.workload == "exact" and not os.environ.get("ORZ_BENCH_NO_DECODE"):
+        dec_rec = decode_subrecord(np.asarray(streams[0]), want, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -476,19 +355,25 @@ def main():
     p_launch = sum(parse_launches) / len(parse_launches)
     alg_bytes = total_in + comp_bytes  # encode = N_in read + N_out written
     achieved = alg_bytes / (p_ms / 1e3) / 1e9
-    # stage A kernel of this run (mirrors launch_parse in encode_kernels.cu): one stream -> v4, several -> v3
-    parse_ver = int(os.environ.get("ORZ_B200_PARSE", "4" if n == 1 else "3"))
-    parse_kernel = {3: "orz_parse_kernel", 4: "orz_parse4_kernel", 5: "orz_parse5_kernel", 6: "orz_parse6_kernel"}.get(parse_ver, "?")
+    # stage A kernel of this run (mirrors launch_parse in encode_kernels.cu / batch_create in capi.cu)
+    if decode_dir:
+        kernel = "orz_decode_kernel"
+    elif n <= 8 and not os.environ.get("ORZ_B200_LEGACY_STAGE_A"):
+        kernel = "orz_parse7_kernel<16,%s>" % os.environ.get("ORZ_B200_V7_CLUSTER", "8")
+    else:
+        kernel = "orz_parse4_kernel<16,4>" if n == 1 else ("orz_parse_kernel<22,16>" if n <= 296 else "orz_parse_kernel<11,8>")
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(parse_kernel + "_dram_bytes_per_launch")  # null until that kernel has an ncu capture
+            traffic = json.load(open(tp)).get(kernel.split("<")[0] + "_dram_bytes_per_launch")  # from one ncu --set full capture
         except Exception:
             traffic = None
     out = dict(base)
-    out["config"] = dict(config, stage_a={"kernel": parse_kernel, "switches": dict(tuned) if tuned else "library default",
-                                          "selection": tune_state})
+    out["config"] = dict(config, stage_a=kernel, bit_identical_to_oracle=identical,
+                         oracle_pin="two independent restatements agree; NOT pinned against real orz bytes (no Rust toolchain; tools/make_ref_golden.sh)")
+    if identical is False:
+        out["invalid"] = "the timed stream differs from the oracle's"
     out.update({
         "value": plain_all / step_s / 1e6,
         "ms_per_step": step_s * 1e3,
@@ -496,43 +381,100 @@ def main():
                 "d2h_bytes_per_step": out_all},
         "gpu_launches": int(sum(launches)),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "orz_decode_kernel" if decode_dir else parse_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes / p_launch, "launches_per_step": p_launch,
                      "avg_launch_ms": p_ms / p_launch,
-                     "note": "latency-bound serial parse: one warp per stream; the fraction is expected to be ~1e-6..1e-4"},
+                     "note": "one orz stream is ONE serial dependency chain (SURVEY 0-2): the kernel is bound by dependent-instruction and "
+                             "shared-memory latency of the resolver warp, not by HBM; the fraction is expected to be ~1e-6..1e-5"},
         "kernel_ms_per_step": ({"decode": p_ms} if decode_dir else {"parse": p_ms, "emit": sum(emit_ms) / len(emit_ms)}),
         "compressed_bytes": total_in if decode_dir else comp_bytes,
     })
-    # CPU baseline: the oracle on this box's host cores, one stream = one core (the reference is single-threaded)
-    if n_gpus == 1:
-        from oracle import pyoracle
-        pyoracle.build()
-        sample = (raw_streams[0] if decode_dir else streams[0]) if args.workload == "exact" else data
-        best = None
-        want = None
-        for _ in range(2):
-            if decode_dir:
-                comp0 = pyoracle.encode(sample, LEVEL) if args.workload != "exact" else streams[0]
-                t0 = time.perf_counter()
-                want = pyoracle.decode(comp0, int(np.asarray(sample).size) + 64)
-            else:
-                t0 = time.perf_counter()
-                want = pyoracle.encode(sample, LEVEL)
-            dt = time.perf_counter() - t0
-            best = dt if best is None or dt < best else best
-        ours = batch.download(0) if args.workload == "exact" else None
-        out["bit_identical_to_oracle"] = (ours == want) if ours is not None else None
-        out["cpu_baseline"] = {"value": int(np.asarray(sample).size) / best / 1e6, "unit": "MB/s", "cores": 1, "kind": "port",
-                               "sample": f"the whole {int(np.asarray(sample).size):,} B corpus as one stream, best of 2, C oracle "
-                                         f"(port of the reference; Rust cannot be built here); host has {os.cpu_count()} cores"}
-    if n_gpus == 1 and args.workload == "exact" and not decode_dir and not os.environ.get("ORZ_BENCH_NO_VARIANTS"):
-        for k in tuned:  # the side measurements compare with the library's own default
-            os.environ.pop(k, None)
-        out["stage_a_variants"] = probe_variants(done=tune_results)
+    if identical is not None:
+        out["bit_identical_to_oracle"] = identical
+    if n_gpus == 1 and args.workload == "exact":
+        nb = int(np.asarray(sample).size)
+        out["cpu_baseline"] = {"value": nb / cpu_s / 1e6, "unit": "MB/s", "cores": 1, "kind": "port",
+                               "sample": f"the whole {nb:,} B corpus as one stream, one pass, C oracle (port of the reference; Rust cannot "
+                                         f"be built here); host has {os.cpu_count()} cores"}
+    if seg_rec:
+        out["segments"] = seg_rec
+    if dec_rec:
+        out["decode"] = dec_rec
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+SEG_BYTES = 1 << 24
+SEG_COPIES = 8
+
+
+def segments_subrecord(torch, dist, rank, world, dev, corpus):
+    """enwik8 x 8 (800 MB) cut into 16 MiB segments = independent orz streams (fresh LZEncoder each, lib.rs:64), segment i on rank
+    i % N, every rank encodes its shard resident in HBM, ONE gather of the spans at the end (orz_b200.dist.gather_spans).  Strong
+    scaling: the work is fixed, value = 800 MB / max-over-ranks time.  Rank 0 checks its first and last segment against the oracle."""
+    import hashlib
+    from orz_b200 import Batch
+    from orz_b200 import dist as odist
+    from oracle import pyoracle
+    total = corpus.size * SEG_COPIES
+    nseg = (total + SEG_BYTES - 1) // SEG_BYTES
+
+    def seg(i):  # bytes [i*SEG, (i+1)*SEG) of the corpus repeated SEG_COPIES times
+        lo, hi = i * SEG_BYTES, min((i + 1) * SEG_BYTES, total)
+        idx = np.arange(lo, hi, dtype=np.int64) % corpus.size
+        return corpus[idx]
+    mine = odist.shard_streams(nseg, rank, world)
+    segs = [seg(i) for i in mine]
+    b = Batch(Batch.ENCODE, [int(s.size) for s in segs], cfg=LEVEL, device=dev)
+    for i, s in enumerate(segs):
+        b.upload(i, s)
+    device = torch.device("cuda", dev)
+    times = []
+    for it in range(2):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        b.run()
+        if dist is not None:
+            spans = [odist.device_span(b.result_dev(i), b.result_len(i), device) for i in range(len(segs))]
+            odist.gather_spans(spans, device)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    sec = times[-1]
+    ok = None
+    if rank == 0 and segs:
+        ok = all(hashlib.sha256(b.download(j)).digest() == hashlib.sha256(pyoracle.encode(segs[j], LEVEL)).digest() for j in {0, len(segs) - 1})
+    comp = sum(b.result_len(i) for i in range(len(segs)))
+    b.close()
+    if dist is not None:
+        t = torch.tensor([sec], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t[0])
+        cb = torch.tensor([comp], dtype=torch.float64, device=device)
+        dist.all_reduce(cb, op=dist.ReduceOp.SUM)
+        comp = int(cb[0])
+    return {"value": total / sec / 1e6, "unit": "MB/s", "scaling": "strong", "bytes": int(total), "segments": int(nseg), "segment_bytes": SEG_BYTES,
+            "level": LEVEL, "ms": sec * 1e3, "compressed_bytes": comp, "sample_identical_to_oracle": ok,
+            "what": "BASELINE configs[2]/[3] shape: independent 16 MiB segments sharded i % N, one final gather of the spans; second of two passes, "
+                    "inputs resident in HBM, wall clock around a device sync, max over ranks"}
+
+
+def decode_subrecord(plain, comp, dev):
+    """BASELINE configs[4] at its smallest size: the oracle-compressed corpus decoded as one exact stream on one GPU."""
+    from orz_b200 import Batch
+    comp = np.frombuffer(comp, dtype=np.uint8)
+    b = Batch(Batch.DECODE, [int(comp.size)], out_caps=[int(plain.size) + 64], device=dev)
+    b.upload(0, comp)
+    b.run()
+    b.run()
+    ms, _ = b.timing(4)
+    got = b.download(0)
+    b.close()
+    return {"value": plain.size / (ms / 1e3) / 1e6, "unit": "MB/s", "ms": ms, "bit_identical": got == plain.tobytes(),
+            "what": "decode of the oracle's -l2 stream of the corpus, one stream, second of two passes, CUDA events on the library's stream"}
 
 
 if __name__ == "__main__":

@@ -57,7 +57,7 @@ namespace orz {
 constexpr int kListCap = 64;           // entries per key list (circular, newest at (count-1) % 64)
 constexpr int kMaxDepth7 = 48;         // deepest LZCfg depth this kernel handles (levels 0-2 use 45)
 constexpr int kRing7 = 512;            // probe record slots in CTA 0's shared memory
-constexpr uint32_t kLeadTarget7 = 128; // how far ahead of the parse records are built: every position of lead is a chance to go stale
+constexpr uint32_t kLeadTarget7 = 96; // how far ahead of the parse records are built: every position of lead is a chance to go stale
 constexpr int kExtCand = 48;           // candidates per record kept for repairs
 constexpr int kSumWords = 12;          // summary words per record
 constexpr int kExtWords = 2 + kExtCand; // F_ext, ord0, candidates
@@ -158,6 +158,9 @@ struct ParseShared7 {
 //  6  F: the record is exact for every decision time T >= F as long as no step in [F, T) has its key
 //  7  words update if a literal is emitted here: hash2 index | value << 15   (lz.rs:233)
 //  8  words update if the match is emitted here                               (lz.rs:208)
+
+// warp maximum of small non-negative values (LCPs; -1 = none) with one REDUX instead of five shuffles
+__device__ __forceinline__ int warp_max_u(int v) { return (int)__reduce_max_sync(kFull, (unsigned)(v + 1)) - 1; }
 
 struct FmState {
     int max_len;
@@ -298,8 +301,8 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
     if (ok1) lcp1 = lcp_win_win(win, p1, y);
     ORZ_COST(500);
     // lazy maxima (matcher.rs:194-228 restated: has_lazy_match(min_len) <=> longest LCP among the first `depth` nodes >= min_len)
-    int m1 = warp_max(max((ok0 && lane < B.depth1) ? lcp0 : -1, (ok1 && 32 + lane < B.depth1) ? lcp1 : -1));
-    int m2 = warp_max(max((ok0 && lane < B.depth2) ? lcp0 : -1, (ok1 && 32 + lane < B.depth2) ? lcp1 : -1));
+    int m1 = warp_max_u(max((ok0 && lane < B.depth1) ? lcp0 : -1, (ok1 && 32 + lane < B.depth1) ? lcp1 : -1));
+    int m2 = warp_max_u(max((ok0 && lane < B.depth2) ? lcp0 : -1, (ok1 && 32 + lane < B.depth2) ? lcp1 : -1));
     // find_match (matcher.rs:135-192)
     FmState st;
     st.max_len = kMatchMin - 1;
@@ -373,13 +376,20 @@ struct ByteSrc7 {
         }
         return ld_u32_unaligned(win, p);
     }
+    __device__ __forceinline__ uint32_t ring_u32(uint32_t p) const {
+        const uint32_t w0 = ring[(p >> 2) & (kInRing / 4 - 1)], w1 = ring[((p >> 2) + 1) & (kInRing / 4 - 1)];
+        return __funnelshift_r(w0, w1, (p & 3u) * 8u);
+    }
     // mem.rs:41-51 restated byte-exact: longest common prefix of [a..) and [b..), capped at 240
     __device__ __forceinline__ int lcp(uint32_t a, uint32_t b) const {
-        for (int i = 0; i < kMatchMax; i += 4) {
-            const uint32_t x = u32(a + i) ^ u32(b + i);
-            if (x) return i + ((__ffs(x) - 1) >> 3);
+        if (a >= lo && b >= lo && a + 248 <= hi && b + 248 <= hi) { // both ranges sit in the ring
+            for (int i = 0; i < kMatchMax; i += 4) {
+                const uint32_t x = ring_u32(a + i) ^ ring_u32(b + i);
+                if (x) return i + ((__ffs(x) - 1) >> 3);
+            }
+            return kMatchMax;
         }
-        return kMatchMax;
+        return lcp_win_win(win, a, b);
     }
 };
 
@@ -421,6 +431,15 @@ __device__ __forceinline__ bool repair_record7(ParseShared7 &shl, const Build7 &
         if (__ballot_sync(kFull, !inrange)) reached = true;
     }
     if (!reached || k > 32u) return false;
+    if (k == 0) { // the key-hash table aliased: nothing decided since F_ext has this key
+        const uint32_t om = rs[5];
+        if (om == kNone || ((bc - 1 - om) & kOrdMask) <= (uint32_t)(kRing - 1)) {
+            __syncwarp();
+            if (lane == 0) rs[6] = T;
+            __syncwarp();
+            return true;
+        }
+    }
     __syncwarp();
     // ---- 2. merged candidate sequence, 32 per round: lanes < k hold the recent steps (round 0), the others the record's candidates
     int dmax = B.depth0 > B.depth1 ? B.depth0 : B.depth1;
@@ -459,8 +478,8 @@ __device__ __forceinline__ bool repair_record7(ParseShared7 &shl, const Build7 &
         const unsigned vm = __ballot_sync(kFull, valid);
         const int nv = vm == 0xffffffffu ? 32 : (__ffs(~vm) - 1); // alive candidates form a prefix
         valid = lane < nv;
-        m1 = max(m1, warp_max((valid && m < B.depth1) ? lcp : -1));
-        m2 = max(m2, warp_max((valid && m < B.depth2) ? lcp : -1));
+        m1 = max(m1, warp_max_u((valid && m < B.depth1) ? lcp : -1));
+        m2 = max(m2, warp_max_u((valid && m < B.depth2) ? lcp : -1));
         const int before = st.best;
         fm_round(st, valid && m < B.depth0, lcp, exp, m, lane, [&](int ml) {
             const uint32_t p = recent ? cpos : ldcg_u32(&gx[m - (int)k]);
