@@ -136,7 +136,7 @@ struct ParseShared7 {
     uint32_t cnt[kNumCtx];                  // committer: items per rank-coder context in this chunk
     uint32_t inring[kInRing / 4];           // window bytes around the parse position (byte p at p % 4096), kept by the feeder warp
     uint32_t rc_pos[32], rc_exp[32], rc_ord[32]; // repair scratch: recent steps with the record's key
-    uint32_t sbk[64], sbw[64];              // resolver scoreboards: lowest lane of the window that posted this key / words index
+    uint32_t steps[32][8];                  // the super-window's steps: x, type|advance|lengths, key, key+1, key+2, words update, hash2|bytes, matched ordinal
     uint32_t lcnt[kNumBuckets], icnt[kNumBuckets]; // the committers' own insert counts (they number the inserts of a batch in order)
     uint32_t spos;                          // parse position (resolver -> builders)
     uint32_t fpos;                          // every step at a position < fpos is committed to HBM (committer -> builders)
@@ -158,6 +158,7 @@ struct ParseShared7 {
 //  6  F: the record is exact for every decision time T >= F as long as no step in [F, T) has its key
 //  7  words update if a literal is emitted here: hash2 index | value << 15   (lz.rs:233)
 //  8  words update if the match is emitted here                               (lz.rs:208)
+//  9  LCP maxima without the last candidate: find_match's (depth0 - 1) | depth1 - 1 << 8 | depth2 - 1 << 16
 
 // warp maximum of small non-negative values (LCPs; -1 = none) with one REDUX instead of five shuffles
 __device__ __forceinline__ int warp_max_u(int v) { return (int)__reduce_max_sync(kFull, (unsigned)(v + 1)) - 1; }
@@ -303,6 +304,11 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
     // lazy maxima (matcher.rs:194-228 restated: has_lazy_match(min_len) <=> longest LCP among the first `depth` nodes >= min_len)
     int m1 = warp_max_u(max((ok0 && lane < B.depth1) ? lcp0 : -1, (ok1 && 32 + lane < B.depth1) ? lcp1 : -1));
     int m2 = warp_max_u(max((ok0 && lane < B.depth2) ? lcp0 : -1, (ok1 && 32 + lane < B.depth2) ? lcp1 : -1));
+    // the same maxima over one candidate fewer (and the plain LCP maximum of find_match's candidates): what a repair needs when
+    // exactly one newer node of this key has appeared since the frontier (it takes the first place of the sequence)
+    const int mf = warp_max_u(max((ok0 && lane < B.depth0 - 1) ? lcp0 : -1, (ok1 && 32 + lane < B.depth0 - 1) ? lcp1 : -1));
+    const int m1m = warp_max_u(max((ok0 && lane < B.depth1 - 1) ? lcp0 : -1, (ok1 && 32 + lane < B.depth1 - 1) ? lcp1 : -1));
+    const int m2m = warp_max_u(max((ok0 && lane < B.depth2 - 1) ? lcp0 : -1, (ok1 && 32 + lane < B.depth2 - 1) ? lcp1 : -1));
     // find_match (matcher.rs:135-192)
     FmState st;
     st.max_len = kMatchMin - 1;
@@ -357,6 +363,7 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
         sum[6] = F;
         sum[7] = hw_lit | wv_lit << 15;
         sum[8] = hw_m | wv_m << 15;
+        sum[9] = (uint32_t)(mf < 0 ? 0 : mf) | (uint32_t)(m1m < 0 ? 0 : m1m) << 8 | (uint32_t)(m2m < 0 ? 0 : m2m) << 16;
     }
     // the barrier orders every lane's stores before lane 0's release store of the stamp (cumulative: no fence per lane)
     __syncwarp();
@@ -441,6 +448,38 @@ __device__ __forceinline__ bool repair_record7(ParseShared7 &shl, const Build7 &
         }
     }
     __syncwarp();
+    if (k == 1) {
+        // ---- exactly one newer node q1 of this key, every candidate of the record still alive: q1 is tried first (matcher.rs:149).
+        // If it ends the search at once (lcp 240, or longer than its own expected length: matcher.rs:162-167) or no other
+        // candidate is longer, the result is q1 — no need to go through the sequence.
+        const uint32_t om = rs[5];
+        const bool alive = om == kNone || ((bc - 1 - om) & kOrdMask) <= (uint32_t)(kRing - 1);
+        const uint32_t q1 = shl.rc_pos[0], e1 = shl.rc_exp[0], o1 = shl.rc_ord[0], mx = rs[9];
+        const uint32_t l1 = (uint32_t)src.lcp(q1, y);
+        const uint32_t fmmax = B.depth0 >= 2 ? (mx & 0xffu) : 0u;
+        if (alive && B.depth0 >= 1 && l1 >= (uint32_t)kMatchMin && (l1 == (uint32_t)kMatchMax || (e1 > 0 && l1 > e1) || l1 >= fmmax)) {
+            const uint32_t mlen = y + l1 < B.sbuf_len ? l1 : 0u; // matcher.rs:183
+            const uint32_t z1 = B.depth1 >= 1 ? (B.depth1 >= 2 && ((mx >> 8) & 0xffu) > l1 ? (mx >> 8) & 0xffu : l1) : 0u;
+            const uint32_t z2 = B.depth2 >= 1 ? (B.depth2 >= 2 && ((mx >> 16) & 0xffu) > l1 ? (mx >> 16) & 0xffu : l1) : 0u;
+            uint32_t hw_m = 0, wv_m = 0;
+            if (mlen > 0) { // lz.rs:208
+                const uint32_t t4 = src.u32(y + mlen - 5), t2 = src.u32(y + mlen - 2);
+                const uint32_t x3 = (t4 >> 16) & 0xffu, x4 = (t4 >> 8) & 0xffu, x5 = t4 & 0xffu;
+                hw_m = (x3 & 0x7fu) | ((x4 & 0x7fu) | is_alnum(x5) << 7) << 7;
+                wv_m = t2 & 0xffffu;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                rs[3] = mlen | (z1 > 255u ? 255u : z1) << 8 | (z2 > 255u ? 255u : z2) << 16 | (mlen ? e1 : 0u) << 24;
+                rs[4] = o1;
+                if (om == kNone) rs[5] = o1;
+                rs[6] = T;
+                rs[8] = hw_m | wv_m << 15;
+            }
+            __syncwarp();
+            return true;
+        }
+    }
     // ---- 2. merged candidate sequence, 32 per round: lanes < k hold the recent steps (round 0), the others the record's candidates
     int dmax = B.depth0 > B.depth1 ? B.depth0 : B.depth1;
     dmax = dmax > B.depth2 ? dmax : B.depth2;
@@ -549,7 +588,6 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
     if (active && rank == 0) {
         for (int i = tid; i < kNumCtx; i += NT) shl.cnt[i] = 0;
         for (int i = tid; i < kNumBuckets; i += NT) shl.bcnt[i] = shl.lcnt[i] = shl.icnt[i] = S->bcnt[i];
-        for (int i = tid; i < 64; i += NT) shl.sbk[i] = shl.sbw[i] = 0xffffffffu;
         for (int i = tid; i < 4096; i += NT) shl.lastkey[i] = 0;
         for (int i = tid; i < kRing7; i += NT) shl.sum[i][0] = kNone;
         for (int i = tid; i < 32768 / 8; i += NT) reinterpret_cast<uint4 *>(shl.words)[i] = reinterpret_cast<const uint4 *>(S->words)[i];
@@ -593,7 +631,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
             uint32_t spos = S->spos;
             uint32_t after_literal = S->after_literal;
             uint32_t n_items = 0, qhead = 0;
-            unsigned long long n_windows = 0, n_wait = 0, n_repair = 0, n_rep_rec = 0, n_rep_hard = 0, n_cut = 0;
+            unsigned long long n_windows = 0, n_wait = 0, n_repair = 0, n_rep_rec = 0, n_rep_hard = 0, n_cut = 0, n_handed = 0;
             long long cyc_wait = 0, cyc_walk = 0, cyc_commit = 0, cyc_repair = 0, cyc_load = 0;
             unsigned long long lag_steps = 0, lag_pos = 0;
             const long long t_begin = STATS ? clock64() : 0;
@@ -601,118 +639,112 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
             int wd_code = 0;
             unsigned idle = 0;
             uint32_t qlimit = (uint32_t)kQueue7 - 8u; // queue entries below this index are free (consumers re-read when it is reached)
+            const uint32_t last_pos = sbuf_len + 1; // the last position that has a record
             while (spos < sbuf_len && n_items < items_cap) {
+                // ======== one super-window: up to 32 steps, gathered by passes over 30 positions each, then verified and handed over
+                // with lane = step.  Every decision of the super-window is taken against the tables as they stand at its start;
+                // the verification below finds the first step that an earlier step of the same super-window would have changed.
                 const long long t0 = STATS ? clock64() : 0;
-                const uint32_t x = spos + (uint32_t)lane;
-                const uint32_t *rs = shl.sum[slot7<NBW>(x)];
-                // ---- load this lane's record.  The stamp is the builder's last store (release); the first 16 bytes are read in
-                // one shared-memory transaction, the rest afterwards, so a matching stamp covers every field.
-                const uint4 a = lds_volatile_v4(rs);
-                const uint4 b = lds_volatile_v4(rs + 4);
-                const uint32_t wmat = ld_vol_u32(rs + 8);
-                const bool ready = a.x == x;
-                const uint32_t last_pos = sbuf_len + 1; // the last position that has a record
-                const uint32_t key = a.y & 0x1fffffu, c = key >> 13;
-                const bool incomplete = (a.y >> 27) & 1u;
-                const uint32_t h2 = a.z & 0x7fffu, b2 = a.z >> 15;
-                const uint32_t mlen = a.w & 0xffu, wexp = a.w >> 24;
-                const uint32_t word = b.x, ordmin = b.y, F = b.z, wlit = b.w;
-                const uint32_t lwe = shl.words[h2];                            // lz.rs:132
-                const uint32_t bc = shl.bcnt[c];
-                const uint32_t kh = (key ^ (key >> 9)) & 4095u;
-                const uint32_t lk = shl.lastkey[kh];
-                // exactness of the record at decision time (see the header): no step with this key since F, oldest candidate alive.
-                // `tight`: fewer than 32 further inserts keep the oldest candidate alive — exact only for the window's first step.
-                const int room = ordmin == kNone ? 64 : (int)(kRing - 1) - (int)((bc - 1 - ordmin) & kOrdMask);
-                const bool stale = ready && (lk >= F || incomplete || room < 0);
-                const bool tight = ready && room < 32;
-                // neighbours: lane+1 supplies the depth1 lazy maximum, lane+2 the depth2 one (lz.rs:154-169)
-                const uint32_t nb = ((a.w >> 8) & 0xffffu) | (stale ? 1u : 0u) << 16 | (ready ? 0u : 1u) << 17 | (tight ? 1u : 0u) << 18;
-                const uint32_t nb1 = __shfl_down_sync(kFull, nb, 1), nb2 = __shfl_down_sync(kFull, nb, 2);
-                const uint32_t key1 = __shfl_down_sync(kFull, key, 1), key2 = __shfl_down_sync(kFull, key, 2);
-                const uint32_t lzn1 = nb1 & 0xffu, lzn2 = (nb2 >> 8) & 0xffu;
-                const bool lzneed = mlen > 0 && mlen < (uint32_t)(kMatchMax / 2);
-                const bool has1 = lane < 31 && x + 1 <= last_pos, has2 = lane < 30 && x + 2 <= last_pos;
-                // the step this lane takes IF it is on the path and nothing decided in this window before it interferes
-                const uint32_t lwm = lwe == b2 ? 1u : 0u;                       // lz.rs:133
-                const uint32_t ro0 = (bc - 1 - word) & kOrdMask;                // reduced offset with no further insert before it (matcher.rs:185)
-                const uint32_t rb = ro0 < 510u ? 1u : 0u;                       // robitlen < 8  <=>  reduced offset < 510
-                const bool rbsens = mlen > 0 && rb && ro0 + 31u >= 510u;        // an insert of this window could flip robitlen < 8
-                const uint32_t dec = decide7(mlen, lzn1, lzn2, lwm, rb, x + 1 < sbuf_len);
-                const uint32_t ty = dec >> 8, adv = dec & 0xffu;
-                // what the chase sees: advance (clamped to the window's end) | type << 8; type 3 ends the window at this lane:
-                // code 1 = a record must be repaired first, 2 = a record is not built yet, 3 = plain window boundary
-                const bool nr = !ready || (has1 && ((nb1 >> 17) & 1u)) || (has2 && ((nb2 >> 17) & 1u));
-                const bool rep = stale || (lzneed && ((has1 && ((nb1 >> 16) & 1u)) || (has2 && ((nb2 >> 16) & 1u))));
-                // a record whose oldest candidate is within 32 inserts of leaving the ring, or whose robitlen < 8 an insert could
-                // flip, is exact only for the window's FIRST step: later lanes end the window there
-                const bool edge = lane > 0 && (tight || rbsens || (lzneed && ((has1 && ((nb1 >> 18) & 1u)) || (has2 && ((nb2 >> 18) & 1u)))));
-                uint32_t pk = (adv + (uint32_t)lane > 32u ? 32u - (uint32_t)lane : adv) | ty << 8;
-                if (nr) pk = 2u | 3u << 8;
-                else if (rep) pk = 1u | 3u << 8;
-                else if (edge || (lane >= 30 && x + 2 <= last_pos) || x >= sbuf_len) pk = 3u | 3u << 8;
-                const uint32_t wu = ty == kTyWord ? 0xffffffffu : (ty == kTyMatch ? wmat : wlit); // lz.rs:208,233
-                const long long t1 = STATS ? clock64() : 0;
-                if (STATS) cyc_load += t1 - t0;
-
-                // ---- chase the step chain through the window (lz.rs:131-236): one shuffle per step, nothing else on the chain
-                uint32_t path = 0, cur = 0;
+                const uint32_t max_steps = items_cap - n_items < 32u ? items_cap - n_items : 32u;
+                uint32_t nst = 0, base = spos;
                 int stop = 0;
-                for (;;) {
-                    const uint32_t v = __shfl_sync(kFull, pk, cur);
-                    if (v >= 0x300u) {
-                        stop = (int)(v & 0xffu);
+                for (;;) { // ---- passes
+                    const uint32_t x = base + (uint32_t)lane;
+                    const uint32_t *rs = shl.sum[slot7<NBW>(x)];
+                    // The stamp is the builder's last store (release); the first 16 bytes are read in one shared-memory transaction,
+                    // the rest afterwards, so a matching stamp covers every field.
+                    const uint4 a = lds_volatile_v4(rs);
+                    const uint4 b = lds_volatile_v4(rs + 4);
+                    const uint32_t wmat = ld_vol_u32(rs + 8);
+                    const bool ready = a.x == x;
+                    const uint32_t key = a.y & 0x1fffffu, c = key >> 13;
+                    const bool incomplete = (a.y >> 27) & 1u;
+                    const uint32_t h2 = a.z & 0x7fffu, b2 = a.z >> 15;
+                    const uint32_t mlen = a.w & 0xffu, wexp = a.w >> 24;
+                    const uint32_t word = b.x, ordmin = b.y, F = b.z, wlit = b.w;
+                    const uint32_t lwe = shl.words[h2];                            // lz.rs:132
+                    const uint32_t bc = shl.bcnt[c];
+                    const uint32_t kh = (key ^ (key >> 9)) & 4095u;
+                    const uint32_t lk = shl.lastkey[kh];
+                    // exactness of the record at decision time (see the header): no step with this key since F, oldest candidate alive.
+                    // `tight`: fewer than 32 further inserts keep the oldest candidate alive — exact only for the super-window's first step.
+                    const int room = ordmin == kNone ? 64 : (int)(kRing - 1) - (int)((bc - 1 - ordmin) & kOrdMask);
+                    const bool stale = ready && (lk >= F || incomplete || room < 0);
+                    const bool tight = ready && room < 32;
+                    // neighbours: lane+1 supplies the depth1 lazy maximum, lane+2 the depth2 one (lz.rs:154-169)
+                    const uint32_t nb = ((a.w >> 8) & 0xffffu) | (stale ? 1u : 0u) << 16 | (ready ? 0u : 1u) << 17 | (tight ? 1u : 0u) << 18;
+                    const uint32_t nb1 = __shfl_down_sync(kFull, nb, 1), nb2 = __shfl_down_sync(kFull, nb, 2);
+                    const uint32_t key1 = __shfl_down_sync(kFull, key, 1), key2 = __shfl_down_sync(kFull, key, 2);
+                    const uint32_t lzn1 = nb1 & 0xffu, lzn2 = (nb2 >> 8) & 0xffu;
+                    const bool lzneed = mlen > 0 && mlen < (uint32_t)(kMatchMax / 2);
+                    const bool has1 = lane < 31 && x + 1 <= last_pos, has2 = lane < 30 && x + 2 <= last_pos;
+                    const uint32_t lwm = lwe == b2 ? 1u : 0u;                       // lz.rs:133
+                    const uint32_t ro0 = (bc - 1 - word) & kOrdMask;                // reduced offset with no further insert before it (matcher.rs:185)
+                    const uint32_t rb = ro0 < 510u ? 1u : 0u;                       // robitlen < 8  <=>  reduced offset < 510
+                    const bool rbsens = mlen > 0 && rb && ro0 + 31u >= 510u;        // an insert of this super-window could flip robitlen < 8
+                    const uint32_t dec = decide7(mlen, lzn1, lzn2, lwm, rb, x + 1 < sbuf_len);
+                    const uint32_t ty = dec >> 8, adv = dec & 0xffu;
+                    // what the chase sees: advance (clamped to the pass) | type << 8; type 3 ends the pass at this lane:
+                    // code 1 = a record must be repaired first, 2 = a record is not built yet, 3 = next pass, 4 = end of the super-window
+                    const bool first = nst == 0 && lane == 0;
+                    const bool nr = !ready || (has1 && ((nb1 >> 17) & 1u)) || (has2 && ((nb2 >> 17) & 1u));
+                    const bool rep = stale || (lzneed && ((has1 && ((nb1 >> 16) & 1u)) || (has2 && ((nb2 >> 16) & 1u))));
+                    // a record whose oldest candidate is within 32 inserts of leaving the ring, or whose robitlen < 8 an insert could
+                    // flip, is exact only for the FIRST step of a super-window
+                    const bool edge = !first && (tight || rbsens || (lzneed && ((has1 && ((nb1 >> 18) & 1u)) || (has2 && ((nb2 >> 18) & 1u)))));
+                    uint32_t pk = (adv + (uint32_t)lane > 32u ? 32u - (uint32_t)lane : adv) | ty << 8;
+                    if (nr) pk = 2u | 3u << 8;
+                    else if (rep) pk = 1u | 3u << 8;
+                    else if (edge || x >= sbuf_len) pk = 4u | 3u << 8;
+                    else if (lane >= 30 && x + 2 <= last_pos) pk = 3u | 3u << 8;
+                    const uint32_t wu = ty == kTyWord ? 0xffffffffu : (ty == kTyMatch ? wmat : wlit); // lz.rs:208,233
+
+                    // ---- chase the step chain through the pass (lz.rs:131-236): one shuffle per step, nothing else on the chain
+                    uint32_t path = 0, cur = 0;
+                    int code = 0;
+                    for (;;) {
+                        const uint32_t v = __shfl_sync(kFull, pk, cur);
+                        if (v >= 0x300u) {
+                            code = (int)(v & 0xffu);
+                            break;
+                        }
+                        path |= 1u << cur;
+                        cur += v & 0xffu;
+                        if (cur & 32u) break;
+                    }
+                    uint32_t np = (uint32_t)__popc(path);
+                    if (nst + np > max_steps) { // keep only the steps that still fit (the chunk's item limit, lz.rs:131, or 32)
+                        uint32_t keep = path;
+                        for (uint32_t i = np; nst + i > max_steps; i--) keep &= ~(1u << (31 - __clz(keep)));
+                        cur = (uint32_t)(__ffs(path & ~keep) - 1); // the first step that no longer fits
+                        path = keep;
+                        np = (uint32_t)__popc(path);
+                        code = 4;
+                    }
+                    // ---- the steps of this pass, in step order, for the verification and the hand-over
+                    if ((path >> lane) & 1u) {
+                        uint32_t *e = shl.steps[nst + (uint32_t)__popc(path & lt_mask)];
+                        *reinterpret_cast<uint4 *>(e) = make_uint4(x, ty | (lzneed ? 4u : 0u) | adv << 8 | mlen << 16 | wexp << 24, key, key1);
+                        *reinterpret_cast<uint4 *>(e + 4) = make_uint4(key2, wu, h2 | (lwe & 0xffu) << 16 | (b2 & 0xffu) << 24, word);
+                    }
+                    nst += np;
+                    if (np > 0 && (cur & 32u)) { // the last step leaves the pass: its true advance (the chase value was clamped)
+                        const int lastl = 31 - __clz(path);
+                        cur = (uint32_t)lastl + __shfl_sync(kFull, adv, lastl);
+                    }
+                    base += cur;
+                    if (code == 1 || code == 2 || code == 4) {
+                        stop = code;
                         break;
                     }
-                    path |= 1u << cur;
-                    cur += v & 0xffu;
-                    if (cur & 32u) break;
+                    if (nst >= max_steps || base >= sbuf_len) break;
                 }
-                // the chunk's item limit (lz.rs:131): keep only the steps that still fit
-                const uint32_t max_steps = items_cap - n_items;
-                if ((uint32_t)__popc(path) > max_steps) {
-                    uint32_t keep = path;
-                    for (uint32_t i = (uint32_t)__popc(path); i > max_steps; i--) keep &= ~(1u << (31 - __clz(keep)));
-                    cur = (uint32_t)(__ffs(path & ~keep) - 1); // the first step that no longer fits
-                    path = keep;
-                    stop = 0;
-                }
-                // ---- verify: a step is exact only if no EARLIER step of this window touched what it read — its own or its lazy
-                // neighbours' candidate lists (same key) or its words entry — and no two steps write the same words entry.  Every step
-                // posts its key and its words index in two 64-entry scoreboards (the lowest lane wins); a step that finds an earlier
-                // lane under one of its own indices ends the window and becomes the first step of the next one.  Scoreboard
-                // aliases only cut windows short, they never change a decision.
-                const bool onp = (path >> lane) & 1u;
-                if (path & (path - 1)) { // two or more steps
-                    const uint32_t sk = kh & 63u, sw = wu & 63u, sr = h2 & 63u;
-                    if (onp) {
-                        atomicMin(&shl.sbk[sk], (uint32_t)lane);
-                        if (wu != 0xffffffffu) atomicMin(&shl.sbw[sw], (uint32_t)lane);
-                    }
-                    __syncwarp();
-                    const uint32_t k1h = (key1 ^ (key1 >> 9)) & 63u, k2h = (key2 ^ (key2 >> 9)) & 63u;
-                    bool viol = shl.sbk[sk] < (uint32_t)lane || shl.sbw[sr] < (uint32_t)lane || (wu != 0xffffffffu && shl.sbw[sw] < (uint32_t)lane);
-                    if (lzneed) viol = viol || shl.sbk[k1h] < (uint32_t)lane || shl.sbk[k2h] < (uint32_t)lane;
-                    const unsigned vm = __ballot_sync(kFull, viol) & path;
-                    if (onp) { // leave the scoreboards clean
-                        shl.sbk[sk] = 0xffffffffu;
-                        if (wu != 0xffffffffu) shl.sbw[sw] = 0xffffffffu;
-                    }
-                    if (vm) {
-                        const int v = __ffs(vm) - 1;
-                        path &= (1u << v) - 1u;
-                        cur = (uint32_t)v;
-                        stop = 0;
-                        if (STATS) n_cut++;
-                    }
-                }
-                const uint32_t nsteps = (uint32_t)__popc(path);
-                const long long t2 = STATS ? clock64() : 0;
+                const long long t1 = STATS ? clock64() : 0;
                 if (STATS) {
-                    cyc_walk += t2 - t1;
+                    cyc_walk += t1 - t0;
                     n_windows++;
                 }
-                if (nsteps == 0 && stop == 2) { // the next step's records are not there yet
+                if (nst == 0 && stop == 2) { // the next step's records are not there yet
                     if (STATS) {
                         n_wait++;
                         cyc_wait += clock64() - t0;
@@ -726,53 +758,77 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 }
                 idle = 0;
 
-                // ---- hand the decided steps to the committers and fold them into the shared tables
-                if (nsteps > 0) {
-                    const bool onpath = (path >> lane) & 1u;
-                    if (qhead + nsteps > qlimit) { // queue space: both committers must have passed the entries about to be overwritten
+                if (nst > 0) {
+                    __syncwarp();
+                    // ---- verify, lane = step: a step is exact only if no EARLIER step of this super-window touched what it read — its own
+                    // or its lazy neighbours' candidate lists (same key) or its words entry — and no two steps write the same words
+                    // entry.  The first step that fails ends the super-window and becomes the first step of the next one.
+                    const bool live = (uint32_t)lane < nst;
+                    uint4 e0 = make_uint4(0, 0, 0, 0), e1 = make_uint4(0, 0xffffffffu, 0, 0);
+                    if (live) {
+                        e0 = *reinterpret_cast<const uint4 *>(shl.steps[lane]);
+                        e1 = *reinterpret_cast<const uint4 *>(shl.steps[lane] + 4);
+                    }
+                    const uint32_t x = e0.x, ty = e0.y & 3u, lzn = (e0.y >> 2) & 1u, adv = (e0.y >> 8) & 0xffu, mlen = (e0.y >> 16) & 0xffu, wexp = e0.y >> 24;
+                    const uint32_t key = e0.z, key1 = e0.w, key2 = e1.x, wu = e1.y, h2 = e1.z & 0x7fffu, word = e1.w;
+                    bool viol = false;
+                    for (uint32_t j = 0; j + 1 < nst; j++) {
+                        const uint32_t kj = shl.steps[j][2], wj = shl.steps[j][5]; // (broadcast loads)
+                        if (j < (uint32_t)lane) {
+                            const uint32_t wi = wj & 0x7fffu;
+                            viol = viol || kj == key || (lzn && (kj == key1 || kj == key2)) ||
+                                   (wj != 0xffffffffu && (wi == h2 || (wu != 0xffffffffu && wi == (wu & 0x7fffu))));
+                        }
+                    }
+                    const unsigned vm = __ballot_sync(kFull, viol && live);
+                    uint32_t nok = nst;
+                    if (vm) {
+                        nok = (uint32_t)(__ffs(vm) - 1);
+                        base = __shfl_sync(kFull, x, (int)nok); // the failed step starts the next super-window
+                        stop = 0;
+                        if (STATS) n_cut++;
+                    }
+                    // ---- hand the steps to the committers and fold them into the shared tables
+                    const bool onpath = (uint32_t)lane < nok;
+                    if (qhead + nok > qlimit) { // queue space: both committers must have passed the entries about to be overwritten
                         for (;;) {
                             const uint32_t d1 = bcast0(ld_vol_u32(v_qdone)), d2 = bcast0(ld_vol_u32(v_qitem));
                             qlimit = (d1 < d2 ? d1 : d2) + (uint32_t)kQueue7 - 8u;
-                            if (qhead + nsteps <= qlimit) break;
+                            if (qhead + nok <= qlimit) break;
                             ORZ_POLL();
                         }
                     }
-                    // after_literal of a step = the step before it on the path was a literal (lz.rs:229)
-                    const unsigned below = path & lt_mask;
-                    const int lastl = 31 - __clz(path);
-                    const uint32_t pty = __shfl_sync(kFull, ty, below ? 31 - __clz(below) : lastl);
-                    const uint32_t my_al = below ? (pty == kTyLit ? 1u : 0u) : after_literal;
+                    const uint32_t pty = __shfl_up_sync(kFull, ty, 1);
+                    const uint32_t my_al = lane == 0 ? after_literal : (pty == kTyLit ? 1u : 0u); // lz.rs:229
                     if (onpath) {
-                        const uint32_t qi = qhead + (uint32_t)__popc(below);
                         uint4 rec;
                         rec.x = x | ty << 25 | my_al << 27;
                         rec.y = word;                                   // ordinal of the matched node; the committers number the inserts
                         rec.z = key | (ty == kTyMatch ? mlen : 0u) << 21;
-                        rec.w = wexp | (lwe & 0xffu) << 8 | (b2 & 0xffu) << 16;
-                        shl.queue[qi % kQueue7] = rec;
-                        atomicAdd(&shl.bcnt[c], 1u);
-                        atomicMax(&shl.lastkey[kh], x);
-                        if (ty != kTyWord) shl.words[wu & 0x7fffu] = (uint16_t)(wu >> 15); // (no two steps of a window share an index)
+                        rec.w = wexp | ((e1.z >> 16) & 0xffu) << 8 | (e1.z >> 24) << 16;
+                        shl.queue[(qhead + (uint32_t)lane) % kQueue7] = rec;
+                        atomicAdd(&shl.bcnt[key >> 13], 1u);
+                        atomicMax(&shl.lastkey[(key ^ (key >> 9)) & 4095u], x);
+                        if (ty != kTyWord) shl.words[wu & 0x7fffu] = (uint16_t)(wu >> 15); // (no two surviving steps share an index)
                     }
-                    after_literal = __shfl_sync(kFull, ty, lastl) == kTyLit ? 1u : 0u;
-                    // the true advance of the last step (its chase value was clamped to the window)
-                    const uint32_t ladv = __shfl_sync(kFull, adv, lastl);
-                    if (!stop && (cur & 32u)) cur = (uint32_t)lastl + ladv;
-                    qhead += nsteps;
-                    n_items += nsteps;
-                    spos += cur;
+                    after_literal = __shfl_sync(kFull, ty, (int)nok - 1) == kTyLit ? 1u : 0u;
+                    (void)adv;
+                    qhead += nok;
+                    n_items += nok;
+                    spos = base;
                     __syncwarp();
                     if (lane == 0) {
                         *v_qhead = qhead;
                         *v_spos = spos;
                     }
                     if (STATS) {
+                        n_handed += nok;
                         lag_steps += qhead - ld_vol_u32(v_qdone);
                         lag_pos += spos - ld_vol_u32(&shl.fpos);
                     }
                 }
                 const long long t3 = STATS ? clock64() : 0;
-                if (STATS) cyc_commit += t3 - t2;
+                if (STATS) cyc_commit += t3 - t1;
                 if (stop == 1 && spos < sbuf_len && n_items < items_cap) {
                     // ---- REPAIR: the record of spos (or of a lazy neighbour it needs) is stale.  Re-resolve it in place from the step
                     // log (repair_record7); a record that cannot be repaired that way is rebuilt from HBM after the committer drained.
