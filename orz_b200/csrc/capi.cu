@@ -13,8 +13,9 @@
 #include <vector>
 
 namespace orz {
-void launch_parse(EncStream *, int, bool v7, cudaStream_t);
-void launch_emit(EncStream *, int, cudaStream_t);
+void launch_parse(EncStream *, int, bool v7, int buf, cudaStream_t);
+void launch_emit(EncStream *, int, int buf, cudaStream_t);
+void launch_chunk_done(EncStream *, int, int buf, cudaStream_t);
 void launch_enc_begin(EncStream *, int, cudaStream_t);
 void launch_enc_advance(EncStream *, int, cudaStream_t);
 void launch_enc_forward(EncStream *, uint32_t, bool v7, cudaStream_t);
@@ -117,6 +118,8 @@ struct orz_batch {
     int n = 0;
     orz_lzcfg cfg{};
     cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr;      // v7 encode: stages B-D of chunk k run here while stage A of chunk k+1 runs on `st`
+    cudaEvent_t ev_parse[2] = {nullptr, nullptr}, ev_emit[2] = {nullptr, nullptr};
     uint8_t *arena = nullptr;
     size_t arena_size = 0;
     // state region inside the arena that must be reset before each run: [state_off, state_off+state_size)
@@ -198,6 +201,14 @@ static void batch_destroy(orz_batch *b) {
     if (b->st) cudaStreamSynchronize(b->st);
     if (b->arena) cudaFree(b->arena);
     if (b->h_status_pinned) cudaFreeHost(b->h_status_pinned);
+    if (b->st2) {
+        cudaStreamSynchronize(b->st2);
+        cudaStreamDestroy(b->st2);
+    }
+    for (int i = 0; i < 2; i++) {
+        if (b->ev_parse[i]) cudaEventDestroy(b->ev_parse[i]);
+        if (b->ev_emit[i]) cudaEventDestroy(b->ev_emit[i]);
+    }
     if (b->st) cudaStreamDestroy(b->st);
     delete b;
 }
@@ -244,7 +255,7 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
 
     ArenaPlan plan;
     struct Offs {
-        size_t in, out, win, nodes, heads, words, symranks, items, sorted, payload, zero_lo, zero_hi, klist, kcnt, lm, gext;
+        size_t in, out, win, nodes, heads, words, symranks, items, items_alt, sorted, payload, zero_lo, zero_hi, klist, kcnt, lm, gext;
         size_t win_alloc;
         uint32_t win_lo, win_hi, items_cap, payload_cap;
     };
@@ -289,6 +300,7 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
             }
             o.symranks = plan.take(sizeof(SymRank) * kNumCtx);
             o.items = plan.take(sizeof(Item) * o.items_cap);
+            o.items_alt = v7 && !chunk_mode ? plan.take(sizeof(Item) * o.items_cap) : 0;
             o.sorted = plan.take(sizeof(uint32_t) * o.items_cap);
             o.payload = plan.take(o.payload_cap);
         } else {
@@ -309,8 +321,15 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
         delete b;
         return nullptr;
     }
-    if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost(&b->h_status_pinned, sizeof(int32_t) * n) != cudaSuccess) {
+    bool ok2 = true;
+    if (mode == 0 && v7 && !chunk_mode) {
+        ok2 = cudaStreamCreateWithFlags(&b->st2, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 2 && ok2; i++)
+            ok2 = cudaEventCreateWithFlags(&b->ev_parse[i], cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&b->ev_emit[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok2 || cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost(&b->h_status_pinned, sizeof(int32_t) * 2 * n) != cudaSuccess) {
         *err = ORZ_ECUDA;
         batch_destroy(b);
         return nullptr;
@@ -340,6 +359,7 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
             S.words = reinterpret_cast<uint16_t *>(A + o.words);
             S.symranks = reinterpret_cast<SymRank *>(A + o.symranks);
             S.items = reinterpret_cast<Item *>(A + o.items);
+            S.items_alt = v7 && !chunk_mode ? reinterpret_cast<Item *>(A + o.items_alt) : nullptr;
             S.sorted = reinterpret_cast<uint32_t *>(A + o.sorted);
             S.payload = A + o.payload;
             S.payload_cap = o.payload_cap;
@@ -406,12 +426,15 @@ static int batch_reset_state(orz_batch *b) {
 static int fetch_status(orz_batch *b, bool *all_done) {
     const void *src = b->mode == 0 ? (const void *)&b->d_enc[0].status : (const void *)&b->d_dec[0].status;
     const size_t pitch = b->mode == 0 ? sizeof(EncStream) : sizeof(DecStream);
-    CU_TRY(cudaMemcpy2DAsync(b->h_status_pinned, sizeof(int32_t), src, pitch, sizeof(int32_t), b->n, cudaMemcpyDeviceToHost, b->st));
+    // encode: {status, parse_done} are adjacent — a stream whose stage A reached the end of its input needs no further round
+    const size_t width = b->mode == 0 ? 2 * sizeof(int32_t) : sizeof(int32_t);
+    CU_TRY(cudaMemcpy2DAsync(b->h_status_pinned, width, src, pitch, width, b->n, cudaMemcpyDeviceToHost, b->st));
     CU_TRY(cudaStreamSynchronize(b->st));
     *all_done = true;
     for (int i = 0; i < b->n; i++) {
-        b->status[i] = b->h_status_pinned[i];
-        if (b->status[i] == 0) *all_done = false;
+        b->status[i] = b->mode == 0 ? b->h_status_pinned[2 * i] : b->h_status_pinned[i];
+        const bool parsed = b->mode == 0 && b->h_status_pinned[2 * i + 1] != 0;
+        if (b->status[i] == 0 && !parsed) *all_done = false;
     }
     return ORZ_OK;
 }
@@ -445,21 +468,31 @@ extern "C" int orz_batch_run(orz_batch *b) {
         int id = b->timer.begin(2, b->st);
         launch_enc_begin(b->d_enc, b->n, b->st);
         b->timer.end(id, b->st);
-        for (;;) {
-            if ((rc = fetch_status(b, &all_done))) return rc;
+        for (int k = 0;; k++) {
+            if ((rc = fetch_status(b, &all_done))) return rc; // (waits for stage A of the previous round, not for its stages B-D)
             if (all_done) break;
+            const int buf = b->v7 ? (k & 1) : 0;
+            cudaStream_t se = b->v7 ? b->st2 : b->st;
+            if (b->v7 && k >= 2) CU_TRY(cudaStreamWaitEvent(b->st, b->ev_emit[buf], 0)); // the item buffer is free again
             id = b->timer.begin(0, b->st);
-            launch_parse(b->d_enc, b->n, b->v7, b->st);
+            launch_parse(b->d_enc, b->n, b->v7, buf, b->st);
             b->timer.end(id, b->st);
-            id = b->timer.begin(1, b->st);
-            launch_emit(b->d_enc, b->n, b->st);
-            b->timer.end(id, b->st);
-            if (b->v7) { // end of a block: slide + forward + next block's load, grid-wide (no-ops otherwise)
+            if (b->v7) { // the lib.rs:72-89 decision and, at the end of a block, slide + forward + next block's load (grid-wide)
                 id = b->timer.begin(2, b->st);
+                launch_chunk_done(b->d_enc, b->n, buf, b->st);
                 launch_enc_advance(b->d_enc, b->n, b->st);
                 b->timer.end(id, b->st);
+                CU_TRY(cudaEventRecord(b->ev_parse[buf], b->st));
+                CU_TRY(cudaStreamWaitEvent(se, b->ev_parse[buf], 0));
             }
+            id = b->timer.begin(1, se);
+            launch_emit(b->d_enc, b->n, buf, se);
+            b->timer.end(id, se);
+            if (b->v7) CU_TRY(cudaEventRecord(b->ev_emit[buf], se));
             CU_TRY(cudaGetLastError());
+        }
+        if (b->v7) { // the last chunks' stages B-D, then make `st` wait for them too (the timing events of the whole run live there)
+            CU_TRY(cudaStreamSynchronize(b->st2));
         }
         // result lengths
         std::vector<EncStream> tmp(b->n);
@@ -807,8 +840,9 @@ extern "C" int orz_lzenc_encode(orz_lzenc *e, const orz_lzcfg *cfg, const uint8_
     CU_TRY(cudaMemcpyAsync(&b->d_enc[0].spos, ss, sizeof ss, cudaMemcpyHostToDevice, b->st));
     if (b->v7 && (cfg->match_depth > kV7MaxDepth || cfg->lazy_match_depth1 > kV7MaxDepth || cfg->lazy_match_depth2 > kV7MaxDepth))
         return ORZ_EARG; // the key-list layout holds 48 candidates per position (main.rs:97-102 uses at most 45); ORZ_B200_LEGACY_STAGE_A=1 lifts this
-    launch_parse(b->d_enc, 1, b->v7, b->st);
-    launch_emit(b->d_enc, 1, b->st);
+    launch_parse(b->d_enc, 1, b->v7, 0, b->st);
+    if (b->v7) launch_chunk_done(b->d_enc, 1, 0, b->st);
+    launch_emit(b->d_enc, 1, 0, b->st);
     CU_TRY(cudaGetLastError());
     EncStream R;
     CU_TRY(cudaMemcpyAsync(&R, b->d_enc, sizeof R, cudaMemcpyDeviceToHost, b->st));

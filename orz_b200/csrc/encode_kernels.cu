@@ -906,22 +906,23 @@ struct EmitShared {
     uint32_t total_bits;
 };
 
-__global__ void __launch_bounds__(kEmitThreads) orz_emit_kernel(EncStream *streams) {
+__global__ void __launch_bounds__(kEmitThreads) orz_emit_kernel(EncStream *streams, int buf) {
     EncStream *S = &streams[blockIdx.x];
     if (S->status != 0) return;
+    if (S->v7 && S->self_driven && S->chunk_flags[buf] == 2u) return; // nothing was parsed into this buffer
     ORZ_DYN_SHARED(smem_raw);
     EmitShared &sh = *reinterpret_cast<EmitShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    Item *items = S->items;
+    Item *items = buf ? S->items_alt : S->items;
     uint32_t *sorted = S->sorted;
-    const uint32_t n_items = S->n_items;
+    const uint32_t n_items = buf ? S->n_items_alt : S->n_items;
     const bool first_block = S->first_block != 0;
 
     // ---- init shared ----
     for (int i = tid; i < 2 * kSymStride; i += kEmitThreads) (&sh.hist1[0][0])[i] = 0;
     for (int i = tid; i < 256; i += kEmitThreads) sh.hist2[i] = 0;
     for (int i = tid; i < kSymStride; i += kEmitThreads) sh.symcount[i] = 0;
-    for (int i = tid; i < kNumCtx; i += kEmitThreads) sh.cnt[i] = S->ctx_count[i];
+    for (int i = tid; i < kNumCtx; i += kEmitThreads) sh.cnt[i] = (buf ? S->ctx_count_alt : S->ctx_count)[i];
     for (int i = tid; i < kSymStride; i += kEmitThreads) sh.rcp[i] = i < 2 ? 0u : (uint32_t)(((1ull << 32) + (unsigned)i - 1) / (unsigned)i);
     if (tid == 0) sh.next_ctx = 0;
     __syncthreads();
@@ -1111,7 +1112,8 @@ __global__ void __launch_bounds__(kEmitThreads) orz_emit_kernel(EncStream *strea
             bw.varint(sh.num_counted);
             for (uint32_t k = 0; k < sh.num_counted; k++) bw.put(sh.vs[k], 9);
         }
-        const uint32_t end_spos = S->spos < S->sbuf_len ? S->spos : S->sbuf_len;
+        // (v7: stage A of the next chunk may already be moving spos; the chunk's own end was recorded by orz_chunk_done_kernel)
+        const uint32_t end_spos = S->v7 ? S->chunk_end_spos[buf] : (S->spos < S->sbuf_len ? S->spos : S->sbuf_len);
         bw.varint(end_spos);
         bw.varint(n_items);
         write_huffman_table(bw, sh.lens[0], kNumSym);
@@ -1223,11 +1225,23 @@ __global__ void __launch_bounds__(kEmitThreads) orz_emit_kernel(EncStream *strea
     __syncthreads();
 
     // ---- block loop (lib.rs:72-86): next chunk, or slide + forward + next block, or EOF ----
-    const uint32_t spos = S->spos, sbuf_len = S->sbuf_len;
     if (!fits) {
         if (tid == 0) S->status = -2; // ORZ_ENOSPC
         return;
     }
+    if (S->v7) { // the loop state moved on with stage A (orz_chunk_done_kernel + advance kernels); only the end marker is left
+        if (tid == 0) {
+            if (S->chunk_flags[buf] & 1u) { // lib.rs:89: empty chunk marks EOF
+                S->out[opos] = 0;
+                S->out_pos = opos + 1;
+                S->status = 1;
+            } else {
+                S->out_pos = opos;
+            }
+        }
+        return;
+    }
+    const uint32_t spos = S->spos, sbuf_len = S->sbuf_len;
     if (spos < sbuf_len) {
         if (tid == 0) S->out_pos = opos;
         return;
@@ -1238,13 +1252,6 @@ __global__ void __launch_bounds__(kEmitThreads) orz_emit_kernel(EncStream *strea
             S->out[opos] = 0;
             S->out_pos = opos + 1;
             S->status = 1;
-        }
-        return;
-    }
-    if (S->v7) { // slide, forward and the next block's load run grid-wide in orz_enc_advance_kernel
-        if (tid == 0) {
-            S->out_pos = opos;
-            S->need_slide = 1;
         }
         return;
     }
@@ -1319,6 +1326,32 @@ __global__ void __launch_bounds__(256) orz_enc_forward_kernel(EncStream *streams
 }
 
 size_t emit_smem_bytes() { return sizeof(EmitShared); }
+
+// After stage A of a chunk (v7 streams, one thread per stream): records what stages B-D need of the loop state and takes the
+// lib.rs:72-89 decision — next chunk, end of the block (the advance kernels follow) or end of the stream — so that stage A of
+// the next chunk does not wait for stages B-D of this one.
+__global__ void orz_chunk_done_kernel(EncStream *streams, int nstreams, int buf) {
+    const int si = blockIdx.x * blockDim.x + threadIdx.x;
+    if (si >= nstreams) return;
+    EncStream *S = &streams[si];
+    if (S->status != 0 || !S->v7) return;
+    if (S->parse_done) { // an earlier chunk was the stream's last: nothing was parsed into this buffer
+        S->chunk_flags[buf] = 2u;
+        return;
+    }
+    const uint32_t spos = S->spos, sbuf_len = S->sbuf_len;
+    S->chunk_end_spos[buf] = spos < sbuf_len ? spos : sbuf_len;
+    uint32_t flags = 0;
+    if (S->self_driven && spos >= sbuf_len) {
+        if (S->in_pos >= S->in_len) {
+            flags = 1u;
+            S->parse_done = 1;
+        } else {
+            S->need_slide = 1;
+        }
+    }
+    S->chunk_flags[buf] = flags;
+}
 
 // End of a block for v7 streams (lib.rs:83-84,72), grid-wide.  phase 0: slide the window (copy_within(len-PREMATCH.., 0)) and
 // rebase the key lists (LZEncoder::forward, lz.rs:82-87); phase 1: read the next block into [PREMATCH, PREMATCH+rd).
@@ -1403,15 +1436,15 @@ static void launch_parse4_variant(EncStream *d_streams, int n, cudaStream_t st) 
 }
 
 template <int NW, int K, bool STATS>
-static void launch_parse7_variant(EncStream *d_streams, int n, cudaStream_t st) {
+static void launch_parse7_variant(EncStream *d_streams, int n, int buf, cudaStream_t st) {
     static_assert(sizeof(ParseShared7) <= 227 * 1024, "stage A v7: shared memory of CTA 0 exceeds an SM");
     auto kern = orz_parse7_kernel<NW, K, STATS>;
     set_smem_attr(kern, sizeof(ParseShared7));
 #ifndef ORZ_SIMT_EMU
     if (K > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
 #endif
-    if (K > 1) ORZ_LAUNCH_CLUSTER(kern, n * K, NW * 32, sizeof(ParseShared7), st, K, d_streams);
-    else ORZ_LAUNCH(kern, n, NW * 32, sizeof(ParseShared7), st, d_streams);
+    if (K > 1) ORZ_LAUNCH_CLUSTER(kern, n * K, NW * 32, sizeof(ParseShared7), st, K, d_streams, buf);
+    else ORZ_LAUNCH(kern, n, NW * 32, sizeof(ParseShared7), st, d_streams, buf);
 }
 
 // Library configuration, read once per process:
@@ -1443,17 +1476,17 @@ bool parse7_stats_enabled() { return lib_cfg().stats; }
 // Stage A.  v7: the stream arena holds key lists (parse_v7.cuh: one cluster per stream).  Otherwise ring records +
 // hash chains: one stream runs v4 (windowed resolver, 16 warps), several streams run the v3 kernel (one executor thread + 8 or
 // 16 builder warps per stream), whose many-stream throughput is the measured one.
-void launch_parse(EncStream *d_streams, int n, bool v7, cudaStream_t st) {
+void launch_parse(EncStream *d_streams, int n, bool v7, int buf, cudaStream_t st) {
     const LibCfg &c = lib_cfg();
     if (v7) {
         if (c.stats) {
-            if (c.cluster == 16) launch_parse7_variant<16, 16, true>(d_streams, n, st);
-            else if (c.cluster == 1) launch_parse7_variant<16, 1, true>(d_streams, n, st);
-            else launch_parse7_variant<16, 8, true>(d_streams, n, st);
+            if (c.cluster == 16) launch_parse7_variant<16, 16, true>(d_streams, n, buf, st);
+            else if (c.cluster == 1) launch_parse7_variant<16, 1, true>(d_streams, n, buf, st);
+            else launch_parse7_variant<16, 8, true>(d_streams, n, buf, st);
         } else {
-            if (c.cluster == 16) launch_parse7_variant<16, 16, false>(d_streams, n, st);
-            else if (c.cluster == 1) launch_parse7_variant<16, 1, false>(d_streams, n, st);
-            else launch_parse7_variant<16, 8, false>(d_streams, n, st);
+            if (c.cluster == 16) launch_parse7_variant<16, 16, false>(d_streams, n, buf, st);
+            else if (c.cluster == 1) launch_parse7_variant<16, 1, false>(d_streams, n, buf, st);
+            else launch_parse7_variant<16, 8, false>(d_streams, n, buf, st);
         }
         return;
     }
@@ -1465,10 +1498,11 @@ void launch_parse(EncStream *d_streams, int n, bool v7, cudaStream_t st) {
     if (c.legacy == 3 || (c.legacy == 0 && n <= 2 * 148)) launch_parse_variant<22, 16>(d_streams, n, st);
     else launch_parse_variant<11, 8>(d_streams, n, st);
 }
-void launch_emit(EncStream *d_streams, int n, cudaStream_t st) {
+void launch_emit(EncStream *d_streams, int n, int buf, cudaStream_t st) {
     set_smem_attr(orz_emit_kernel, sizeof(EmitShared));
-    ORZ_LAUNCH(orz_emit_kernel, n, kEmitThreads, sizeof(EmitShared), st, d_streams);
+    ORZ_LAUNCH(orz_emit_kernel, n, kEmitThreads, sizeof(EmitShared), st, d_streams, buf);
 }
+void launch_chunk_done(EncStream *d_streams, int n, int buf, cudaStream_t st) { ORZ_LAUNCH(orz_chunk_done_kernel, (n + 63) / 64, 64, 0, st, d_streams, n, buf); }
 void launch_enc_advance(EncStream *d_streams, int n, cudaStream_t st) {
     ORZ_LAUNCH(orz_enc_advance_kernel, 592, 256, 0, st, d_streams, n, 0);
     ORZ_LAUNCH(orz_enc_advance_kernel, 592, 256, 0, st, d_streams, n, 1);

@@ -150,7 +150,8 @@ struct EncStream {
     uint8_t *lm;          // [256][kNodesStride] match_len_min of the node in each ring slot (matcher.rs:231-237)
     uint32_t *gext;       // [512][48] candidate positions of the probe records in flight
     uint32_t v7;          // 1: this stream uses the v7 layout (nodes / heads are not allocated)
-    uint32_t need_slide;  // set by the emit kernel at the end of a block: the advance kernels slide, forward and load
+    uint32_t need_slide;  // set at the end of a block: the advance kernels slide, forward and load
+    Item *items_alt;      // v7: second item buffer — stages B-D of chunk k read one while stage A of chunk k+1 fills the other
     uint32_t dbg_flags;   // measurement switches (ORZ_B200_DBG): 1 no re-stamp, 8 executor cycle counters, 32 builder counters, 64 v3 idle builders sleep
     // mutable
     uint32_t bhead[kNumBuckets];
@@ -160,7 +161,12 @@ struct EncStream {
     uint32_t payload_len;
     uint64_t in_pos, out_pos;
     int32_t status;       // 0 running, 1 done, <0 error code
+    uint32_t parse_done;  // v7: stage A reached the end of the input (the last chunk may still be in stages B-D)
     uint32_t n_chunks;
+    uint32_t n_items_alt;
+    uint32_t chunk_end_spos[2]; // v7, per item buffer: min(spos, sbuf_len) after the chunk (lz.rs:268)
+    uint32_t chunk_flags[2];    // v7, per item buffer: bit 0 = the stream ends after this chunk (lib.rs:89)
+    uint32_t ctx_count_alt[kNumCtx];
     unsigned long long dbg[8]; // stage A counters: steps, executor spin iterations (own / lazy1 / lazy2 probe), builds, aborted builds
     unsigned long long dbg7[16]; // v7: resolver cycles total, load, walk, hand-over, repair, wait; records repaired, rebuilt from HBM; builder cycles; list lag
 };

@@ -136,7 +136,7 @@ struct ParseShared7 {
     uint32_t cnt[kNumCtx];                  // committer: items per rank-coder context in this chunk
     uint32_t inring[kInRing / 4];           // window bytes around the parse position (byte p at p % 4096), kept by the feeder warp
     uint32_t rc_pos[32], rc_exp[32], rc_ord[32]; // repair scratch: recent steps with the record's key
-    uint32_t steps[32][8];                  // the super-window's steps: x, type|advance|lengths, key, key+1, key+2, words update, hash2|bytes, matched ordinal
+    uint32_t steps[32][8];                  // the super-window's steps: x, type|advance|lengths, key of x+1 | literal byte, key of x+2, key, words update, hash2 | words entry read, matched ordinal
     uint32_t lcnt[kNumBuckets], icnt[kNumBuckets]; // the committers' own insert counts (they number the inserts of a batch in order)
     uint32_t spos;                          // parse position (resolver -> builders)
     uint32_t fpos;                          // every step at a position < fpos is committed to HBM (committer -> builders)
@@ -570,10 +570,13 @@ __device__ __forceinline__ uint32_t slot7(uint32_t y) {
 // NW warps per CTA, K CTAs per stream (a thread-block cluster).  CTA 0: warp 0 resolver, warp 1 committer, the warps that
 // do not share the resolver's SM sub-partition build; CTAs 1..K-1: all warps build.
 template <int NW, int K, bool STATS>
-__global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams) {
+__global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams, int buf) {
     constexpr int NT = NW * 32;
     static_assert(NW % 4 == 0 && NW >= 8, "stage A v7: warps per CTA");
-    constexpr int NB0 = NW - 4 - (NW / 4 - 1); // builders in CTA 0: warps >= 4 that do not share the resolver's SM sub-partition
+    // Builders in CTA 0: none when the stream owns a cluster — measured on a B200, every busy warp on the resolver's SM slows the
+    // resolver (shared LSU / shared-memory pipeline): 1225 cycles per step with 9 builders beside it.  A single-CTA launch (K = 1)
+    // has to keep them: warps >= 4 that do not share the resolver's SM sub-partition.
+    constexpr int NB0 = K > 1 ? 0 : NW - 4 - (NW / 4 - 1);
     constexpr int NBW = NB0 + (K - 1) * NW;    // builder warps of the cluster
     constexpr uint32_t kLeadMax = ((uint32_t)kRing7 / NBW) * NBW - 40u;
     constexpr uint32_t kLead = kLeadMax < kLeadTarget7 ? kLeadMax : kLeadTarget7; // builders stay this close to the parse position
@@ -583,7 +586,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
     ParseShared7 &shl = *reinterpret_cast<ParseShared7 *>(smem_raw);
     ParseShared7 &sh = K > 1 ? *map_to_cta0(&shl) : shl; // CTA 0's shared memory (DSMEM for the other CTAs)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool active = S->status == 0; // uniform over the cluster (the status word is not written before the final barrier)
+    const bool active = S->status == 0 && S->parse_done == 0; // uniform over the cluster (the status word is not written before the final barrier)
 
     if (active && rank == 0) {
         for (int i = tid; i < kNumCtx; i += NT) shl.cnt[i] = 0;
@@ -724,8 +727,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                     // ---- the steps of this pass, in step order, for the verification and the hand-over
                     if ((path >> lane) & 1u) {
                         uint32_t *e = shl.steps[nst + (uint32_t)__popc(path & lt_mask)];
-                        *reinterpret_cast<uint4 *>(e) = make_uint4(x, ty | (lzneed ? 4u : 0u) | adv << 8 | mlen << 16 | wexp << 24, key, key1);
-                        *reinterpret_cast<uint4 *>(e + 4) = make_uint4(key2, wu, h2 | (lwe & 0xffu) << 16 | (b2 & 0xffu) << 24, word);
+                        *reinterpret_cast<uint4 *>(e) = make_uint4(x, ty | (lzneed ? 4u : 0u) | adv << 8 | mlen << 16 | wexp << 24, key1 | (b2 & 0xffu) << 21, key2);
+                        *reinterpret_cast<uint4 *>(e + 4) = make_uint4(key, wu, h2 | lwe << 15, word);
                     }
                     nst += np;
                     if (np > 0 && (cur & 32u)) { // the last step leaves the pass: its true advance (the chase value was clamped)
@@ -770,14 +773,19 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                         e1 = *reinterpret_cast<const uint4 *>(shl.steps[lane] + 4);
                     }
                     const uint32_t x = e0.x, ty = e0.y & 3u, lzn = (e0.y >> 2) & 1u, adv = (e0.y >> 8) & 0xffu, mlen = (e0.y >> 16) & 0xffu, wexp = e0.y >> 24;
-                    const uint32_t key = e0.z, key1 = e0.w, key2 = e1.x, wu = e1.y, h2 = e1.z & 0x7fffu, word = e1.w;
+                    const uint32_t key = e1.x, key1 = e0.z & 0x1fffffu, key2 = e0.w, wu = e1.y, h2 = e1.z & 0x7fffu, lwe = e1.z >> 15, word = e1.w;
+                    const uint32_t b2lo = e0.z >> 21;
                     bool viol = false;
-                    for (uint32_t j = 0; j + 1 < nst; j++) {
-                        const uint32_t kj = shl.steps[j][2], wj = shl.steps[j][5]; // (broadcast loads)
+                    uint32_t wnext = 32; // the next step of the super-window that writes the same words entry (the last writer wins)
+                    for (uint32_t j = 0; j < nst; j++) {
+                        const uint2 kw = *reinterpret_cast<const uint2 *>(&shl.steps[j][4]); // (one broadcast load)
+                        const uint32_t kj = kw.x, wj = kw.y;
+                        const uint32_t wi = wj & 0x7fffu;
                         if (j < (uint32_t)lane) {
-                            const uint32_t wi = wj & 0x7fffu;
-                            viol = viol || kj == key || (lzn && (kj == key1 || kj == key2)) ||
-                                   (wj != 0xffffffffu && (wi == h2 || (wu != 0xffffffffu && wi == (wu & 0x7fffu))));
+                            // an earlier step put a node on one of the lists this step read, or changed the words entry it read
+                            viol = viol || kj == key || (lzn && (kj == key1 || kj == key2)) || (wj != 0xffffffffu && wi == h2 && (wj >> 15) != lwe);
+                        } else if (j > (uint32_t)lane && wnext == 32u && wj != 0xffffffffu && wu != 0xffffffffu && wi == (wu & 0x7fffu)) {
+                            wnext = j;
                         }
                     }
                     const unsigned vm = __ballot_sync(kFull, viol && live);
@@ -805,11 +813,11 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                         rec.x = x | ty << 25 | my_al << 27;
                         rec.y = word;                                   // ordinal of the matched node; the committers number the inserts
                         rec.z = key | (ty == kTyMatch ? mlen : 0u) << 21;
-                        rec.w = wexp | ((e1.z >> 16) & 0xffu) << 8 | (e1.z >> 24) << 16;
+                        rec.w = wexp | (lwe & 0xffu) << 8 | b2lo << 16;
                         shl.queue[(qhead + (uint32_t)lane) % kQueue7] = rec;
                         atomicAdd(&shl.bcnt[key >> 13], 1u);
                         atomicMax(&shl.lastkey[(key ^ (key >> 9)) & 4095u], x);
-                        if (ty != kTyWord) shl.words[wu & 0x7fffu] = (uint16_t)(wu >> 15); // (no two surviving steps share an index)
+                        if (ty != kTyWord && wnext >= nok) shl.words[wu & 0x7fffu] = (uint16_t)(wu >> 15);
                     }
                     after_literal = __shfl_sync(kFull, ty, (int)nok - 1) == kTyLit ? 1u : 0u;
                     (void)adv;
@@ -883,7 +891,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 }
                 S->spos = spos;
                 S->after_literal = after_literal;
-                S->n_items = n_items;
+                (buf ? S->n_items_alt : S->n_items) = n_items;
                 if (STATS) {
                     S->dbg[0] += n_items;
                     S->dbg[1] += n_windows;
@@ -916,7 +924,11 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 const uint32_t head = bcast0(ld_vol_u32(v_qhead));
                 if (head == tail) {
                     if (dn) break;
+#ifdef ORZ_SIMT_EMU
                     ORZ_POLL();
+#else
+                    __nanosleep(64);
+#endif
                     continue;
                 }
                 const uint32_t n = head - tail < 32u ? head - tail : 32u;
@@ -961,16 +973,20 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
             // its own pace behind the queue.
             volatile uint32_t *v_qhead = &shl.qhead;
             volatile uint32_t *v_qitem = &shl.qitem;
-            Item *items = S->items;
+            Item *items = buf ? S->items_alt : S->items;
             uint8_t *lmarr = S->lm;
             uint32_t tail = 0;
             const unsigned lt_mask = (1u << lane) - 1u;
             for (;;) {
                 const uint32_t dn = bcast0(ld_vol_u32(v_done));
                 const uint32_t head = bcast0(ld_vol_u32(v_qhead));
-                if (head == tail) {
-                    if (dn) break;
+                if (head == tail || (head - tail < 24u && !dn)) { // (batches of at least 24 steps: fewer, fuller passes)
+                    if (dn && head == tail) break;
+#ifdef ORZ_SIMT_EMU
                     ORZ_POLL();
+#else
+                    __nanosleep(256);
+#endif
                     continue;
                 }
                 const uint32_t n = head - tail < 32u ? head - tail : 32u;
@@ -1092,7 +1108,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
 #ifdef ORZ_SIMT_EMU
                     ORZ_POLL();
 #else
-                    __nanosleep(100);
+                    __nanosleep(400);
 #endif
                     continue;
                 }
@@ -1105,7 +1121,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
                 __syncwarp();
                 if (lane == 0) *v_fed = fed;
             }
-        } else if (rank != 0 || (warp >= 4 && (warp & 3) != 0)) {
+        } else if (rank != 0 || (K == 1 && warp >= 4 && (warp & 3) != 0)) {
             // ============================================================== builders
             int bi;
             if (rank == 0) bi = warp - 4 - warp / 4;
@@ -1149,7 +1165,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams)
     if (K > 1) cluster_barrier(); // no remote builder touches CTA 0's shared memory after this point
     if (active && rank == 0) {
         for (int i = tid; i < 32768 / 8; i += NT) reinterpret_cast<uint4 *>(S->words)[i] = reinterpret_cast<const uint4 *>(shl.words)[i];
-        for (int i = tid; i < kNumCtx; i += NT) S->ctx_count[i] = shl.cnt[i];
+        for (int i = tid; i < kNumCtx; i += NT) (buf ? S->ctx_count_alt : S->ctx_count)[i] = shl.cnt[i];
         for (int i = tid; i < kNumBuckets; i += NT) S->bcnt[i] = shl.bcnt[i];
     }
 }
