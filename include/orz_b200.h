@@ -83,7 +83,9 @@ int orz_lzdec_decode(orz_lzdec *, const uint8_t *tbuf, size_t tlen, uint8_t *sbu
 
 /* =====================================================================================
  * Stream interface — replaces orz::encode / orz::decode (src/lib.rs:58-92, 94-129), memory to memory.
- * Output of orz_encode_stream is byte-identical to `orz encode -l<level>` of the same input.
+ * Output of orz_encode_stream is byte-identical to the in-tree restatements of `orz encode -l<level>` (oracle/orz_oracle.c and the
+ * independent oracle/pyref.py agree on it); parity with bytes produced by a real orz build is NOT pinned yet: no Rust toolchain exists
+ * where this was written (tools/make_ref_golden.sh produces the pin wherever nightly Rust is available).
  * ===================================================================================== */
 size_t orz_encode_bound(size_t n);
 int orz_encode_stream(int device, const orz_lzcfg *cfg, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
@@ -99,6 +101,14 @@ int orz_encode_batch(int device, const orz_lzcfg *cfg, int nstreams, const uint8
                      uint8_t *const *out, const size_t *out_cap, size_t *out_len);
 int orz_decode_batch(int device, int nstreams, const uint8_t *const *in, const size_t *n, uint8_t *const *out,
                      const size_t *out_cap, size_t *out_len);
+
+/* Several GPUs of one box behind the C ABI (no torch, no NCCL needed by the caller): stream i runs on devices[i % ndev], one host
+ * thread per device, results land in the caller's `out[i]` (the "gather" is the D2H copy of each span).  Streams are independent orz
+ * streams exactly as in orz_encode_batch; one orz stream does not shard.  devices[] may repeat an index. */
+int orz_encode_batch_multi(const int *devices, int ndev, const orz_lzcfg *cfg, int nstreams, const uint8_t *const *in, const size_t *n,
+                           uint8_t *const *out, const size_t *out_cap, size_t *out_len);
+int orz_decode_batch_multi(const int *devices, int ndev, int nstreams, const uint8_t *const *in, const size_t *n, uint8_t *const *out,
+                           const size_t *out_cap, size_t *out_len);
 
 /* Device-resident batch: inputs are uploaded once, run() touches only HBM (what bench.py's `value` times),
  * download() brings results back.  mode: 0 = encode, 1 = decode. */

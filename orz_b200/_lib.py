@@ -34,6 +34,7 @@ SYMBOLS = [
     "orz_lzenc_new", "orz_lzenc_free", "orz_lzenc_forward", "orz_lzenc_encode",
     "orz_lzdec_new", "orz_lzdec_free", "orz_lzdec_forward", "orz_lzdec_decode",
     "orz_encode_bound", "orz_encode_stream", "orz_decode_stream", "orz_encode_batch", "orz_decode_batch",
+    "orz_encode_batch_multi", "orz_decode_batch_multi",
     "orz_batch_create", "orz_batch_free", "orz_batch_upload", "orz_batch_run", "orz_batch_result_len",
     "orz_batch_download", "orz_batch_result_dev", "orz_batch_timing",
     "orz_segmented_bound", "orz_encode_segmented", "orz_segmented_raw_len", "orz_decode_segmented",
@@ -74,6 +75,8 @@ def load():
     L.orz_decode_stream.argtypes = [C.c_int, vp, sz, vp, sz, szp]
     L.orz_encode_batch.argtypes = [C.c_int, C.POINTER(LZCfg), C.c_int, C.POINTER(vp), szp, C.POINTER(vp), szp, szp]
     L.orz_decode_batch.argtypes = [C.c_int, C.c_int, C.POINTER(vp), szp, C.POINTER(vp), szp, szp]
+    L.orz_encode_batch_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(LZCfg), C.c_int, C.POINTER(vp), szp, C.POINTER(vp), szp, szp]
+    L.orz_decode_batch_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp), szp, C.POINTER(vp), szp, szp]
     L.orz_batch_create.argtypes = [C.c_int, C.c_int, C.POINTER(LZCfg), C.c_int, szp, szp]
     L.orz_batch_create.restype = vp
     L.orz_batch_free.argtypes = [vp]

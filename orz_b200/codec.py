@@ -62,6 +62,24 @@ def encode_batch(sources, cfg=2, device: int = 0):
     return [outs[i][: outl[i]].tobytes() for i in range(n)]
 
 
+def encode_batch_multi(sources, cfg=2, devices=(0,)):
+    """Independent streams sharded over several GPUs of this box behind the C ABI: stream i on devices[i % len(devices)]."""
+    L = load()
+    cfg = _cfg(cfg)
+    n = len(sources)
+    ins = [_u8(s) for s in sources]
+    caps = [L.orz_encode_bound(a.size) for a in ins]
+    outs = [np.empty(c, dtype=np.uint8) for c in caps]
+    inp = (C.c_void_p * n)(*[a.ctypes.data if a.size else None for a in ins])
+    inl = (C.c_size_t * n)(*[a.size for a in ins])
+    outp = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    outc = (C.c_size_t * n)(*caps)
+    outl = (C.c_size_t * n)()
+    devs = (C.c_int * len(devices))(*devices)
+    check(L.orz_encode_batch_multi(devs, len(devices), C.byref(cfg), n, inp, inl, outp, outc, outl), "encoding failed")
+    return [outs[i][: outl[i]].tobytes() for i in range(n)]
+
+
 def decode_batch(targets, out_caps=None, device: int = 0):
     """Independent streams.  Without explicit capacities the output buffers start at 16x the compressed size and grow 4x on
     ORZ_ENOSPC (ROLZ streams of repetitive data exceed any fixed ratio; the reference writes to a growing Write)."""

@@ -646,6 +646,47 @@ extern "C" int orz_decode_batch(int device, int nstreams, const uint8_t *const *
                                 const size_t *out_cap, size_t *out_len) {
     return run_host_batch(device, 1, nullptr, nstreams, in, n, out, out_cap, out_len);
 }
+// Several devices: stream i -> devices[i % ndev], one host thread per device slot (each drives its own arena through the per-device cache)
+#include <thread>
+static int run_multi(const int *devices, int ndev, int mode, const orz_lzcfg *cfg, int n, const uint8_t *const *in, const size_t *in_len,
+                     uint8_t *const *out, const size_t *out_cap, size_t *out_len) {
+    if (!devices || ndev <= 0 || n <= 0 || !in || !in_len || !out || !out_cap || !out_len) return ORZ_EARG;
+    std::vector<int> rc(ndev, ORZ_OK);
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; d++) {
+        th.emplace_back([&, d]() {
+            std::vector<const uint8_t *> i2;
+            std::vector<size_t> n2, c2, l2;
+            std::vector<uint8_t *> o2;
+            std::vector<int> idx;
+            for (int i = d; i < n; i += ndev) {
+                idx.push_back(i);
+                i2.push_back(in[i]);
+                n2.push_back(in_len[i]);
+                o2.push_back(out[i]);
+                c2.push_back(out_cap[i]);
+            }
+            if (idx.empty()) return;
+            l2.resize(idx.size());
+            rc[d] = run_host_batch(devices[d], mode, cfg, (int)idx.size(), i2.data(), n2.data(), o2.data(), c2.data(), l2.data());
+            if (rc[d] == ORZ_OK)
+                for (size_t k = 0; k < idx.size(); k++) out_len[idx[k]] = l2[k];
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < ndev; d++)
+        if (rc[d] != ORZ_OK) return rc[d];
+    return ORZ_OK;
+}
+extern "C" int orz_encode_batch_multi(const int *devices, int ndev, const orz_lzcfg *cfg, int nstreams, const uint8_t *const *in, const size_t *n,
+                                      uint8_t *const *out, const size_t *out_cap, size_t *out_len) {
+    if (!cfg) return ORZ_EARG;
+    return run_multi(devices, ndev, 0, cfg, nstreams, in, n, out, out_cap, out_len);
+}
+extern "C" int orz_decode_batch_multi(const int *devices, int ndev, int nstreams, const uint8_t *const *in, const size_t *n, uint8_t *const *out,
+                                      const size_t *out_cap, size_t *out_len) {
+    return run_multi(devices, ndev, 1, nullptr, nstreams, in, n, out, out_cap, out_len);
+}
 extern "C" int orz_encode_stream(int device, const orz_lzcfg *cfg, const uint8_t *in, size_t n, uint8_t *out, size_t out_cap,
                                  size_t *out_len) {
     return orz_encode_batch(device, cfg, 1, &in, &n, &out, &out_cap, out_len);

@@ -57,7 +57,7 @@ namespace orz {
 constexpr int kListCap = 64;           // entries per key list (circular, newest at (count-1) % 64)
 constexpr int kMaxDepth7 = 48;         // deepest LZCfg depth this kernel handles (levels 0-2 use 45)
 constexpr int kRing7 = 512;            // probe record slots in CTA 0's shared memory
-constexpr uint32_t kLeadTarget7 = 96; // how far ahead of the parse records are built: every position of lead is a chance to go stale
+constexpr uint32_t kLeadTarget7 = 128; // how far ahead of the parse records are built: every position of lead is a chance to go stale
 constexpr int kExtCand = 48;           // candidates per record kept for repairs
 constexpr int kSumWords = 12;          // summary words per record
 constexpr int kExtWords = 2 + kExtCand; // F_ext, ord0, candidates
@@ -66,6 +66,7 @@ constexpr int kInRing = 4096;           // bytes of the window mirrored in CTA 0
 constexpr uint32_t kInAhead = 1536;    // ... from 2048 bytes behind the parse position to this far ahead of it
 constexpr uint32_t kOrdMask = 0x7fffffffu;
 constexpr uint32_t kTyLit = 0, kTyWord = 1, kTyMatch = 2;
+constexpr int kTeam7 = 4;              // decide warps beside the resolver: 4 x 30 positions per round
 
 // A key list entry: pos:25 | expected(low 7 bits):7  ,  ordinal:31 | expected(bit 7):1
 __device__ __forceinline__ uint2 kentry_make(uint32_t pos, uint32_t exp, uint32_t ord) {
@@ -136,9 +137,14 @@ struct ParseShared7 {
     uint32_t cnt[kNumCtx];                  // committer: items per rank-coder context in this chunk
     uint32_t inring[kInRing / 4];           // window bytes around the parse position (byte p at p % 4096), kept by the feeder warp
     uint32_t rc_pos[32], rc_exp[32], rc_ord[32]; // repair scratch: recent steps with the record's key
-    uint32_t steps[32][8];                  // the super-window's steps: x, type|advance|lengths, key of x+1 | literal byte, key of x+2, key, words update, hash2 | words entry read, matched ordinal
+    // the decide team: block t covers positions team_base + 30 t + lane; for every lane the chase word and the step it would take
+    uint32_t pk_all[kTeam7][32];            // advance clamped to the block | type << 8 | true advance << 16; type 3 = stop code
+    uint32_t ent_all[kTeam7 * 32][8];       // x, type|advance|lengths, key of x+1 | literal byte, key of x+2, key, words update, hash2 | words entry read, matched ordinal
+    uint32_t sidx[32];                      // the super-window's steps: index into ent_all
+    uint2 vkw[32];                          // ... and their (key, words update), for the verification loop
     uint32_t lcnt[kNumBuckets], icnt[kNumBuckets]; // the committers' own insert counts (they number the inserts of a batch in order)
-    uint32_t spos;                          // parse position (resolver -> builders)
+    uint32_t spos;                          // parse position: every step before it is decided for good (resolver -> builders)
+    uint32_t lead_pos;                      // how far the resolver has looked (>= spos; a verification cut may fall back behind it)
     uint32_t fpos;                          // every step at a position < fpos is committed to HBM (committer -> builders)
     uint32_t qhead;                         // steps queued (resolver)
     uint32_t qdone;                         // steps whose list entries are committed (list committer)
@@ -146,6 +152,7 @@ struct ParseShared7 {
     uint32_t done;
     uint32_t fed_hi;                        // inring holds window bytes [max(fed_lo0, fed_hi - 4096), fed_hi)
     uint32_t fed_lo0;
+    uint32_t team_base, team_go, team_done; // round control of the decide team (resolver -> team -> resolver)
 };
 
 // summary words
@@ -201,22 +208,6 @@ __device__ __forceinline__ void fm_round(FmState &st, bool valid, int lcp, uint3
         }
         cur = u;
     }
-}
-
-// lz.rs:146-236 for one position: what the step does given the match, the lazy maxima of the two next positions, the
-// last_word_matched bit and robitlen < 8.  Returns advance | type << 8.
-__device__ __forceinline__ uint32_t decide7(uint32_t mlen, uint32_t lz1, uint32_t lz2, uint32_t lwm, uint32_t rb, bool can_word) {
-    int lazy_id = 0;
-    if (mlen > 0) {
-        if (mlen < (uint32_t)(kMatchMax / 2)) {            // lz.rs:151
-            const uint32_t l1 = mlen + 1 + rb, l2 = l1 - lwm; // lz.rs:152-153
-            if (lz1 >= l1) lazy_id = 1;
-            else if (lz2 >= l2) lazy_id = 2;
-        }
-        if (lazy_id == 0) return mlen | kTyMatch << 8;
-    }
-    if (can_word && lazy_id != 1 && lwm) return 2u | kTyWord << 8; // lz.rs:218
-    return 1u | kTyLit << 8;
 }
 
 struct Build7 {
@@ -567,6 +558,67 @@ __device__ __forceinline__ uint32_t slot7(uint32_t y) {
     return (y % (uint32_t)NBW) * SL + (y / (uint32_t)NBW) % SL;
 }
 
+// One block of the decide team: lane l takes the decision of position base + l against the tables as they stand (lz.rs:131-236),
+// as if it were the next step, and leaves the chase word and the step's data for the resolver.  `block0`: lane 0 of this block is
+// the first step of the super-window (records that are exact only for a first step are usable there).
+template <int NBW>
+__device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t base, bool block0, uint32_t sbuf_len, int lane, uint32_t *pk_out,
+                                              uint32_t (*ent_out)[8]) {
+    const uint32_t x = base + (uint32_t)lane;
+    const uint32_t *rs = shl.sum[slot7<NBW>(x)];
+    // The stamp is the builder's last store (release); the first 16 bytes are read in one shared-memory transaction, the rest
+    // afterwards, so a matching stamp covers every field.
+    const uint4 a = lds_volatile_v4(rs);
+    const uint4 b = lds_volatile_v4(rs + 4);
+    const uint32_t wmat = ld_vol_u32(rs + 8);
+    const bool ready = a.x == x;
+    const uint32_t key = a.y & 0x1fffffu, c = key >> 13;
+    const bool incomplete = (a.y >> 27) & 1u;
+    const uint32_t h2 = a.z & 0x7fffu, b2 = a.z >> 15;
+    const uint32_t mlen = a.w & 0xffu, wexp = a.w >> 24;
+    const uint32_t word = b.x, ordmin = b.y, F = b.z, wlit = b.w;
+    const uint32_t lwe = shl.words[h2];                            // lz.rs:132
+    const uint32_t bc = ld_vol_u32(&shl.bcnt[c]);
+    const uint32_t kh = (key ^ (key >> 9)) & 4095u;
+    const uint32_t lk = ld_vol_u32(&shl.lastkey[kh]);
+    // exactness of the record at decision time (see the header): no step with this key since F, oldest candidate alive.
+    // `tight`: fewer than 32 further inserts keep the oldest candidate alive — exact only for the super-window's first step.
+    // flag bits: 1 = stale (repair), 2 = not built yet, 4 = tight.  (Branch-free on purpose: a warp that is alone on its SM
+    // sub-partition pays a pipeline refill for every divergent branch.)
+    const int room = ordmin == kNone ? 64 : (int)(kRing - 1) - (int)((bc - 1 - ordmin) & kOrdMask);
+    const uint32_t fown = !ready ? 2u : (((lk >= F || incomplete || room < 0) ? 1u : 0u) | (room < 32 ? 4u : 0u));
+    // neighbours: lane+1 supplies the depth1 lazy maximum, lane+2 the depth2 one (lz.rs:154-169)
+    const uint32_t nb = ((a.w >> 8) & 0xffffu) | fown << 16;
+    const uint32_t nb1 = __shfl_down_sync(kFull, nb, 1), nb2 = __shfl_down_sync(kFull, nb, 2);
+    const uint32_t key1 = __shfl_down_sync(kFull, key, 1), key2 = __shfl_down_sync(kFull, key, 2);
+    const uint32_t lzn1 = nb1 & 0xffu, lzn2 = (nb2 >> 8) & 0xffu;
+    const bool lzneed = mlen > 0 && mlen < (uint32_t)(kMatchMax / 2);   // lz.rs:151
+    const uint32_t lwm = lwe == b2 ? 1u : 0u;                       // lz.rs:133
+    const uint32_t ro0 = (bc - 1 - word) & kOrdMask;                // reduced offset with no further insert before it (matcher.rs:185)
+    const uint32_t rb = ro0 < 510u ? 1u : 0u;                       // robitlen < 8  <=>  reduced offset < 510
+    const bool rbsens = mlen > 0 && ro0 < 510u && ro0 + 31u >= 510u; // an insert of this super-window could flip robitlen < 8
+    // lz.rs:146-236, spelled out without branches
+    const uint32_t l1 = mlen + 1 + rb, l2 = l1 - lwm;               // lz.rs:152-153
+    const bool lazy1 = lzneed && lzn1 >= l1;
+    const bool lazy2 = lzneed && !lazy1 && lzn2 >= l2;
+    const bool is_match = mlen > 0 && !lazy1 && !lazy2;
+    const bool is_word = !is_match && x + 1 < sbuf_len && !lazy1 && lwm; // lz.rs:218
+    const uint32_t ty = is_match ? kTyMatch : (is_word ? kTyWord : kTyLit);
+    const uint32_t adv = is_match ? mlen : (is_word ? 2u : 1u);
+    // what the chase sees: advance (clamped to the block) | type << 8 | true advance << 16; type 3 ends the block at this lane:
+    // code 1 = a record must be repaired first, 2 = a record is not built yet, 3 = next block, 4 = end of the super-window.
+    // The records of x+1 / x+2 only matter if the step evaluates lazy matches; a tight record or a robitlen < 8 that an insert could
+    // flip is exact only for the FIRST step of a super-window.
+    const uint32_t m = fown | (lzneed ? ((nb1 | nb2) >> 16) : 0u);
+    const bool first = block0 && lane == 0;
+    const uint32_t scode = (m & 2u) ? 2u : (m & 1u) ? 1u : ((!first && ((m & 4u) || rbsens)) || x >= sbuf_len) ? 4u : lane >= 30 ? 3u : 0u;
+    const uint32_t pk = scode ? (scode | 3u << 8) : ((adv + (uint32_t)lane > 32u ? 32u - (uint32_t)lane : adv) | ty << 8 | adv << 16);
+    const uint32_t wu = ty == kTyWord ? 0xffffffffu : (ty == kTyMatch ? wmat : wlit); // lz.rs:208,233
+    pk_out[lane] = pk;
+    *reinterpret_cast<uint4 *>(ent_out[lane]) = make_uint4(x, ty | (lzneed ? 4u : 0u) | adv << 8 | mlen << 16 | wexp << 24, key1 | (b2 & 0xffu) << 21, key2);
+    *reinterpret_cast<uint4 *>(ent_out[lane] + 4) = make_uint4(key, wu, h2 | lwe << 15, word);
+}
+
 // NW warps per CTA, K CTAs per stream (a thread-block cluster).  CTA 0: warp 0 resolver, warp 1 committer, the warps that
 // do not share the resolver's SM sub-partition build; CTAs 1..K-1: all warps build.
 template <int NW, int K, bool STATS>
@@ -576,7 +628,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
     // Builders in CTA 0: none when the stream owns a cluster — measured on a B200, every busy warp on the resolver's SM slows the
     // resolver (shared LSU / shared-memory pipeline): 1225 cycles per step with 9 builders beside it.  A single-CTA launch (K = 1)
     // has to keep them: warps >= 4 that do not share the resolver's SM sub-partition.
-    constexpr int NB0 = K > 1 ? 0 : NW - 4 - (NW / 4 - 1);
+    constexpr int NB0 = K > 1 ? 0 : NW - 4 - kTeam7 - ((NW - 4 - kTeam7) / 4); // (NW = 16: warps 9, 10, 11, 13, 14, 15)
     constexpr int NBW = NB0 + (K - 1) * NW;    // builder warps of the cluster
     constexpr uint32_t kLeadMax = ((uint32_t)kRing7 / NBW) * NBW - 40u;
     constexpr uint32_t kLead = kLeadMax < kLeadTarget7 ? kLeadMax : kLeadTarget7; // builders stay this close to the parse position
@@ -596,11 +648,15 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
         for (int i = tid; i < 32768 / 8; i += NT) reinterpret_cast<uint4 *>(shl.words)[i] = reinterpret_cast<const uint4 *>(S->words)[i];
         if (tid == 0) {
             shl.spos = S->spos;
+            shl.lead_pos = S->spos;
             shl.fpos = S->spos;
             shl.qhead = 0;
             shl.qdone = 0;
             shl.qitem = 0;
             shl.done = 0;
+            shl.team_go = 0;
+            shl.team_done = 0;
+            shl.team_base = S->spos;
             // the feeder starts 2048 bytes behind the parse position (16-byte aligned, inside the allocated window)
             uint32_t f0 = (S->spos - 2048u) & ~15u;
             const uint32_t wlo = (S->win_lo + 15u) & ~15u;
@@ -641,6 +697,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
             const unsigned lt_mask = (1u << lane) - 1u;
             int wd_code = 0;
             unsigned idle = 0;
+            uint32_t round = 0;
             uint32_t qlimit = (uint32_t)kQueue7 - 8u; // queue entries below this index are free (consumers re-read when it is reached)
             const uint32_t last_pos = sbuf_len + 1; // the last position that has a record
             while (spos < sbuf_len && n_items < items_cap) {
@@ -651,67 +708,30 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 const uint32_t max_steps = items_cap - n_items < 32u ? items_cap - n_items : 32u;
                 uint32_t nst = 0, base = spos;
                 int stop = 0;
-                for (;;) { // ---- passes
-                    const uint32_t x = base + (uint32_t)lane;
-                    const uint32_t *rs = shl.sum[slot7<NBW>(x)];
-                    // The stamp is the builder's last store (release); the first 16 bytes are read in one shared-memory transaction,
-                    // the rest afterwards, so a matching stamp covers every field.
-                    const uint4 a = lds_volatile_v4(rs);
-                    const uint4 b = lds_volatile_v4(rs + 4);
-                    const uint32_t wmat = ld_vol_u32(rs + 8);
-                    const bool ready = a.x == x;
-                    const uint32_t key = a.y & 0x1fffffu, c = key >> 13;
-                    const bool incomplete = (a.y >> 27) & 1u;
-                    const uint32_t h2 = a.z & 0x7fffu, b2 = a.z >> 15;
-                    const uint32_t mlen = a.w & 0xffu, wexp = a.w >> 24;
-                    const uint32_t word = b.x, ordmin = b.y, F = b.z, wlit = b.w;
-                    const uint32_t lwe = shl.words[h2];                            // lz.rs:132
-                    const uint32_t bc = shl.bcnt[c];
-                    const uint32_t kh = (key ^ (key >> 9)) & 4095u;
-                    const uint32_t lk = shl.lastkey[kh];
-                    // exactness of the record at decision time (see the header): no step with this key since F, oldest candidate alive.
-                    // `tight`: fewer than 32 further inserts keep the oldest candidate alive — exact only for the super-window's first step.
-                    const int room = ordmin == kNone ? 64 : (int)(kRing - 1) - (int)((bc - 1 - ordmin) & kOrdMask);
-                    const bool stale = ready && (lk >= F || incomplete || room < 0);
-                    const bool tight = ready && room < 32;
-                    // neighbours: lane+1 supplies the depth1 lazy maximum, lane+2 the depth2 one (lz.rs:154-169)
-                    const uint32_t nb = ((a.w >> 8) & 0xffffu) | (stale ? 1u : 0u) << 16 | (ready ? 0u : 1u) << 17 | (tight ? 1u : 0u) << 18;
-                    const uint32_t nb1 = __shfl_down_sync(kFull, nb, 1), nb2 = __shfl_down_sync(kFull, nb, 2);
-                    const uint32_t key1 = __shfl_down_sync(kFull, key, 1), key2 = __shfl_down_sync(kFull, key, 2);
-                    const uint32_t lzn1 = nb1 & 0xffu, lzn2 = (nb2 >> 8) & 0xffu;
-                    const bool lzneed = mlen > 0 && mlen < (uint32_t)(kMatchMax / 2);
-                    const bool has1 = lane < 31 && x + 1 <= last_pos, has2 = lane < 30 && x + 2 <= last_pos;
-                    const uint32_t lwm = lwe == b2 ? 1u : 0u;                       // lz.rs:133
-                    const uint32_t ro0 = (bc - 1 - word) & kOrdMask;                // reduced offset with no further insert before it (matcher.rs:185)
-                    const uint32_t rb = ro0 < 510u ? 1u : 0u;                       // robitlen < 8  <=>  reduced offset < 510
-                    const bool rbsens = mlen > 0 && rb && ro0 + 31u >= 510u;        // an insert of this super-window could flip robitlen < 8
-                    const uint32_t dec = decide7(mlen, lzn1, lzn2, lwm, rb, x + 1 < sbuf_len);
-                    const uint32_t ty = dec >> 8, adv = dec & 0xffu;
-                    // what the chase sees: advance (clamped to the pass) | type << 8; type 3 ends the pass at this lane:
-                    // code 1 = a record must be repaired first, 2 = a record is not built yet, 3 = next pass, 4 = end of the super-window
-                    const bool first = nst == 0 && lane == 0;
-                    const bool nr = !ready || (has1 && ((nb1 >> 17) & 1u)) || (has2 && ((nb2 >> 17) & 1u));
-                    const bool rep = stale || (lzneed && ((has1 && ((nb1 >> 16) & 1u)) || (has2 && ((nb2 >> 16) & 1u))));
-                    // a record whose oldest candidate is within 32 inserts of leaving the ring, or whose robitlen < 8 an insert could
-                    // flip, is exact only for the FIRST step of a super-window
-                    const bool edge = !first && (tight || rbsens || (lzneed && ((has1 && ((nb1 >> 18) & 1u)) || (has2 && ((nb2 >> 18) & 1u)))));
-                    uint32_t pk = (adv + (uint32_t)lane > 32u ? 32u - (uint32_t)lane : adv) | ty << 8;
-                    if (nr) pk = 2u | 3u << 8;
-                    else if (rep) pk = 1u | 3u << 8;
-                    else if (edge || x >= sbuf_len) pk = 4u | 3u << 8;
-                    else if (lane >= 30 && x + 2 <= last_pos) pk = 3u | 3u << 8;
-                    const uint32_t wu = ty == kTyWord ? 0xffffffffu : (ty == kTyMatch ? wmat : wlit); // lz.rs:208,233
-
-                    // ---- chase the step chain through the pass (lz.rs:131-236): one shuffle per step, nothing else on the chain
-                    uint32_t path = 0, cur = 0;
+                // ---- the decide team takes the decision of the next kTeam7 * 30 positions, one block per warp, all at once
+                if (lane == 0) {
+                    shl.team_done = 0;
+                    shl.team_base = spos;
+                    __threadfence_block();
+                    *reinterpret_cast<volatile uint32_t *>(&shl.team_go) = ++round;
+                }
+                while (bcast0(ld_vol_u32(&shl.team_done)) != (uint32_t)kTeam7) ORZ_POLL();
+                const long long tq = STATS ? clock64() : 0;
+                if (STATS) cyc_load += tq - t0;
+                // ---- chase the step chain through the blocks (lz.rs:131-236): one shuffle per step, nothing else on the chain
+                uint32_t rel = 0; // position of the chase relative to spos
+                for (uint32_t t = 0, cur = 0;;) {
+                    const uint32_t pk = ld_vol_u32(&shl.pk_all[t][lane]);
+                    uint32_t path = 0, vlast = 0;
                     int code = 0;
                     for (;;) {
                         const uint32_t v = __shfl_sync(kFull, pk, cur);
-                        if (v >= 0x300u) {
+                        if ((v & 0xff00u) == 0x300u) {
                             code = (int)(v & 0xffu);
                             break;
                         }
                         path |= 1u << cur;
+                        vlast = v;
                         cur += v & 0xffu;
                         if (cur & 32u) break;
                     }
@@ -723,25 +743,24 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                         path = keep;
                         np = (uint32_t)__popc(path);
                         code = 4;
+                    } else if (np > 0 && (cur & 32u)) { // the last step leaves the block: its true advance (the chase value was clamped)
+                        cur = (uint32_t)(31 - __clz(path)) + ((vlast >> 16) & 0xffu);
                     }
-                    // ---- the steps of this pass, in step order, for the verification and the hand-over
-                    if ((path >> lane) & 1u) {
-                        uint32_t *e = shl.steps[nst + (uint32_t)__popc(path & lt_mask)];
-                        *reinterpret_cast<uint4 *>(e) = make_uint4(x, ty | (lzneed ? 4u : 0u) | adv << 8 | mlen << 16 | wexp << 24, key1 | (b2 & 0xffu) << 21, key2);
-                        *reinterpret_cast<uint4 *>(e + 4) = make_uint4(key, wu, h2 | lwe << 15, word);
-                    }
+                    if ((path >> lane) & 1u) shl.sidx[nst + (uint32_t)__popc(path & lt_mask)] = t * 32u + (uint32_t)lane;
                     nst += np;
-                    if (np > 0 && (cur & 32u)) { // the last step leaves the pass: its true advance (the chase value was clamped)
-                        const int lastl = 31 - __clz(path);
-                        cur = (uint32_t)lastl + __shfl_sync(kFull, adv, lastl);
-                    }
-                    base += cur;
+                    rel = 30u * t + cur;
                     if (code == 1 || code == 2 || code == 4) {
                         stop = code;
                         break;
                     }
-                    if (nst >= max_steps || base >= sbuf_len) break;
+                    t = rel / 30u;
+                    cur = rel - 30u * t;
+                    if (t >= (uint32_t)kTeam7 || nst >= max_steps || spos + rel >= sbuf_len) break;
                 }
+                base = spos + rel;
+                // let the builders move on: their lead is counted from here.  (Not `spos`: a verification cut may fall back behind this
+                // position and take another path, so builders must not skip positions on account of it.)
+                if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&shl.lead_pos) = base;
                 const long long t1 = STATS ? clock64() : 0;
                 if (STATS) {
                     cyc_walk += t1 - t0;
@@ -752,7 +771,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                         n_wait++;
                         cyc_wait += clock64() - t0;
                     }
-                    if (++idle > 400000000u) {
+                    if (++idle > 20000000u) {
                         wd_code = 1;
                         break;
                     }
@@ -769,16 +788,19 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                     const bool live = (uint32_t)lane < nst;
                     uint4 e0 = make_uint4(0, 0, 0, 0), e1 = make_uint4(0, 0xffffffffu, 0, 0);
                     if (live) {
-                        e0 = *reinterpret_cast<const uint4 *>(shl.steps[lane]);
-                        e1 = *reinterpret_cast<const uint4 *>(shl.steps[lane] + 4);
+                        const uint32_t *ent = shl.ent_all[shl.sidx[lane]];
+                        e0 = *reinterpret_cast<const uint4 *>(ent);
+                        e1 = *reinterpret_cast<const uint4 *>(ent + 4);
+                        shl.vkw[lane] = make_uint2(e1.x, e1.y);
                     }
+                    __syncwarp();
                     const uint32_t x = e0.x, ty = e0.y & 3u, lzn = (e0.y >> 2) & 1u, adv = (e0.y >> 8) & 0xffu, mlen = (e0.y >> 16) & 0xffu, wexp = e0.y >> 24;
                     const uint32_t key = e1.x, key1 = e0.z & 0x1fffffu, key2 = e0.w, wu = e1.y, h2 = e1.z & 0x7fffu, lwe = e1.z >> 15, word = e1.w;
                     const uint32_t b2lo = e0.z >> 21;
                     bool viol = false;
                     uint32_t wnext = 32; // the next step of the super-window that writes the same words entry (the last writer wins)
                     for (uint32_t j = 0; j < nst; j++) {
-                        const uint2 kw = *reinterpret_cast<const uint2 *>(&shl.steps[j][4]); // (one broadcast load)
+                        const uint2 kw = shl.vkw[j]; // (one broadcast load)
                         const uint32_t kj = kw.x, wj = kw.y;
                         const uint32_t wi = wj & 0x7fffu;
                         if (j < (uint32_t)lane) {
@@ -828,6 +850,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                     if (lane == 0) {
                         *v_qhead = qhead;
                         *v_spos = spos;
+                        *reinterpret_cast<volatile uint32_t *>(&shl.lead_pos) = spos;
                     }
                     if (STATS) {
                         n_handed += nok;
@@ -1121,10 +1144,38 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 __syncwarp();
                 if (lane == 0) *v_fed = fed;
             }
-        } else if (rank != 0 || (K == 1 && warp >= 4 && (warp & 3) != 0)) {
+        } else if (rank == 0 && warp >= 4 && warp < 4 + kTeam7) {
+            // ============================================================== decide team: warp 4 + t takes block t of every round
+            const uint32_t t = (uint32_t)(warp - 4);
+            uint32_t round = 0;
+            for (;;) {
+                uint32_t g;
+                bool quit = false;
+                for (;;) {
+                    g = bcast0(ld_vol_u32(&shl.team_go));
+                    if (g != round) break;
+                    if (bcast0(ld_vol_u32(v_done))) {
+                        quit = true;
+                        break;
+                    }
+#ifdef ORZ_SIMT_EMU
+                    ORZ_POLL();
+#else
+                    __nanosleep(20);
+#endif
+                }
+                if (quit) break;
+                round = g;
+                const uint32_t tb = bcast0(ld_vol_u32(&shl.team_base));
+                decide_block7<NBW>(shl, tb + 30u * t, t == 0, sbuf_len, lane, shl.pk_all[t], &shl.ent_all[t * 32u]);
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) atomicAdd(&shl.team_done, 1u);
+            }
+        } else if (rank != 0 || (K == 1 && warp >= 4 + kTeam7 && (warp & 3) != 0)) {
             // ============================================================== builders
             int bi;
-            if (rank == 0) bi = warp - 4 - warp / 4;
+            if (rank == 0) bi = warp - 4 - kTeam7 - (warp - 4 - kTeam7 + 3) / 4;
             else bi = NB0 + ((int)rank - 1) * NW + warp;
             unsigned long long nbuild = 0;
             long long cyc_build = 0;
@@ -1134,8 +1185,10 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
             for (;;) {
                 if (bcast0(ld_vol_u32(v_done))) break;
                 const uint32_t sp = bcast0(ld_vol_u32(v_spos));
-                if (y < sp) y += ((sp - y + (uint32_t)NBW - 1) / (uint32_t)NBW) * (uint32_t)NBW; // the parse went past: skip
-                if (y > last_pos || y > sp + kLead) {
+                const uint32_t lp = bcast0(ld_vol_u32(&sh.lead_pos));
+                if (y < sp) y += ((sp - y + (uint32_t)NBW - 1) / (uint32_t)NBW) * (uint32_t)NBW; // the parse went past for good: skip
+                // (kLeadMax from `spos` keeps the slot of y - NBW * SL behind everything a fall-back could still need)
+                if (y > last_pos || y > (lp > sp ? lp : sp) + kLead || y > sp + kLeadMax) {
 #ifdef ORZ_SIMT_EMU
                     ORZ_POLL();
 #else

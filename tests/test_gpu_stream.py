@@ -164,3 +164,19 @@ def test_eight_builder_variant_and_wide_batch(monkeypatch):
     for i in (0, 1, 57, 123, 299):
         assert encs[i] == pyoracle.encode(segs[i], 1)
     assert orz_b200.decode_batch(encs, [len(s) + 64 for s in segs]) == segs
+
+
+def test_multi_device_entry_points():
+    """orz_encode_batch_multi: streams sharded over a device list behind the C ABI (no torch).  With one GPU the list repeats it (two host
+    threads, one arena each in turn); with two or more every device is used — also the regression test for per-device kernel attributes
+    (cudaFuncAttributeMaxDynamicSharedMemorySize is per device) and the per-device arena cache."""
+    n = orz_b200.device_count()
+    devs = list(range(min(n, 4))) if n >= 2 else [0, 0]
+    datas = [datagen.text_like(400_000 + 50_000 * i, seed=300 + i) for i in range(5)] + [b"", b"x"]
+    got = orz_b200.encode_batch_multi(datas, 1, devices=devs)
+    for g, d in zip(got, datas):
+        assert g == pyoracle.encode(d, 1)
+    if n >= 2:  # the same process, device 0 then device 1, plain single-device calls
+        assert orz_b200.encode(datas[0], 2, device=0) == pyoracle.encode(datas[0], 2)
+        assert orz_b200.encode(datas[1], 2, device=1) == pyoracle.encode(datas[1], 2)
+        assert orz_b200.decode(pyoracle.encode(datas[2], 0), device=1) == datas[2]
