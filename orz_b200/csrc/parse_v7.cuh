@@ -67,6 +67,7 @@ constexpr uint32_t kInAhead = 1536;    // ... from 2048 bytes behind the parse p
 constexpr uint32_t kOrdMask = 0x7fffffffu;
 constexpr uint32_t kTyLit = 0, kTyWord = 1, kTyMatch = 2;
 constexpr int kTeam7 = 4;              // decide warps beside the resolver: 4 x 30 positions per round
+constexpr int kTeamThreads = (kTeam7 + 1) * 32; // ... and the resolver: the threads of the two round barriers
 
 // A key list entry: pos:25 | expected(low 7 bits):7  ,  ordinal:31 | expected(bit 7):1
 __device__ __forceinline__ uint2 kentry_make(uint32_t pos, uint32_t exp, uint32_t ord) {
@@ -87,6 +88,23 @@ __device__ __forceinline__ T *map_to_cta0(T *p) { return cooperative_groups::thi
 __device__ __forceinline__ void cluster_barrier() { cooperative_groups::this_cluster().sync(); }
 __device__ __forceinline__ unsigned cluster_cta_rank() { return cooperative_groups::this_cluster().block_rank(); }
 #endif
+
+// Named barriers (PTX bar.sync / bar.arrive): a warp that waits at one takes no issue slot and makes no shared-memory traffic —
+// unlike a polling loop, which measurably slows a resolver warp on the same SM.
+__device__ __forceinline__ void bar_sync7(int id, int nthreads) {
+#ifdef ORZ_SIMT_EMU
+    simt::named_barrier(id, nthreads, true);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
+__device__ __forceinline__ void bar_arrive7(int id, int nthreads) {
+#ifdef ORZ_SIMT_EMU
+    simt::named_barrier(id, nthreads, false);
+#else
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
 
 // cluster-scope acquire / release on generic addresses (CTA 0's shared memory seen from any CTA of the cluster)
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
@@ -152,7 +170,7 @@ struct ParseShared7 {
     uint32_t done;
     uint32_t fed_hi;                        // inring holds window bytes [max(fed_lo0, fed_hi - 4096), fed_hi)
     uint32_t fed_lo0;
-    uint32_t team_base, team_go, team_done; // round control of the decide team (resolver -> team -> resolver)
+    uint32_t team_base;                     // first position of the decide team's round (the rounds are paced by named barriers 1 and 2)
 };
 
 // summary words
@@ -654,8 +672,6 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
             shl.qdone = 0;
             shl.qitem = 0;
             shl.done = 0;
-            shl.team_go = 0;
-            shl.team_done = 0;
             shl.team_base = S->spos;
             // the feeder starts 2048 bytes behind the parse position (16-byte aligned, inside the allocated window)
             uint32_t f0 = (S->spos - 2048u) & ~15u;
@@ -697,7 +713,6 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
             const unsigned lt_mask = (1u << lane) - 1u;
             int wd_code = 0;
             unsigned idle = 0;
-            uint32_t round = 0;
             uint32_t qlimit = (uint32_t)kQueue7 - 8u; // queue entries below this index are free (consumers re-read when it is reached)
             const uint32_t last_pos = sbuf_len + 1; // the last position that has a record
             while (spos < sbuf_len && n_items < items_cap) {
@@ -709,13 +724,11 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 uint32_t nst = 0, base = spos;
                 int stop = 0;
                 // ---- the decide team takes the decision of the next kTeam7 * 30 positions, one block per warp, all at once
-                if (lane == 0) {
-                    shl.team_done = 0;
-                    shl.team_base = spos;
-                    __threadfence_block();
-                    *reinterpret_cast<volatile uint32_t *>(&shl.team_go) = ++round;
-                }
-                while (bcast0(ld_vol_u32(&shl.team_done)) != (uint32_t)kTeam7) ORZ_POLL();
+                if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&shl.team_base) = spos;
+                __threadfence_block(); // (bar.arrive itself orders nothing)
+                __syncwarp();
+                bar_arrive7(1, kTeamThreads); // go: the team warps are parked at barrier 1
+                bar_sync7(2, kTeamThreads);   // done: every team warp arrives at barrier 2 when its block is written
                 const long long tq = STATS ? clock64() : 0;
                 if (STATS) cyc_load += tq - t0;
                 // ---- chase the step chain through the blocks (lz.rs:131-236): one shuffle per step, nothing else on the chain
@@ -905,8 +918,11 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 }
             }
             __syncwarp();
+            if (lane == 0) *v_done = 1;
+            __threadfence_block();
+            __syncwarp();
+            bar_arrive7(1, kTeamThreads); // the team wakes up, sees `done` and leaves
             if (lane == 0) {
-                *v_done = 1;
                 if (wd_code) {
                     S->status = -7;
                     S->dbg[6] = (unsigned long long)wd_code;
@@ -950,7 +966,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
 #ifdef ORZ_SIMT_EMU
                     ORZ_POLL();
 #else
-                    __nanosleep(64);
+                    __nanosleep(160);
 #endif
                     continue;
                 }
@@ -1008,7 +1024,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
 #ifdef ORZ_SIMT_EMU
                     ORZ_POLL();
 #else
-                    __nanosleep(256);
+                    __nanosleep(600);
 #endif
                     continue;
                 }
@@ -1131,7 +1147,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
 #ifdef ORZ_SIMT_EMU
                     ORZ_POLL();
 #else
-                    __nanosleep(400);
+                    __nanosleep(800);
 #endif
                     continue;
                 }
@@ -1147,30 +1163,14 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
         } else if (rank == 0 && warp >= 4 && warp < 4 + kTeam7) {
             // ============================================================== decide team: warp 4 + t takes block t of every round
             const uint32_t t = (uint32_t)(warp - 4);
-            uint32_t round = 0;
             for (;;) {
-                uint32_t g;
-                bool quit = false;
-                for (;;) {
-                    g = bcast0(ld_vol_u32(&shl.team_go));
-                    if (g != round) break;
-                    if (bcast0(ld_vol_u32(v_done))) {
-                        quit = true;
-                        break;
-                    }
-#ifdef ORZ_SIMT_EMU
-                    ORZ_POLL();
-#else
-                    __nanosleep(20);
-#endif
-                }
-                if (quit) break;
-                round = g;
+                bar_sync7(1, kTeamThreads); // parked until the resolver starts a round (or ends the launch)
+                if (bcast0(ld_vol_u32(v_done))) break;
                 const uint32_t tb = bcast0(ld_vol_u32(&shl.team_base));
                 decide_block7<NBW>(shl, tb + 30u * t, t == 0, sbuf_len, lane, shl.pk_all[t], &shl.ent_all[t * 32u]);
                 __threadfence_block();
                 __syncwarp();
-                if (lane == 0) atomicAdd(&shl.team_done, 1u);
+                bar_arrive7(2, kTeamThreads);
             }
         } else if (rank != 0 || (K == 1 && warp >= 4 + kTeam7 && (warp & 3) != 0)) {
             // ============================================================== builders

@@ -52,7 +52,7 @@ namespace {
 
 constexpr size_t kStackBytes = 256 * 1024;
 
-enum State { FREE, RUNNABLE, WAIT_WARP, WAIT_BLOCK, WAIT_CLUSTER, DONE };
+enum State { FREE, RUNNABLE, WAIT_WARP, WAIT_BLOCK, WAIT_CLUSTER, WAIT_NAMED, DONE };
 
 struct WarpState;
 struct Block;
@@ -75,11 +75,17 @@ struct WarpState {
     Fiber *lanes[32];
 };
 
+struct NamedBar {
+    int arrived = 0;
+    std::vector<Fiber *> waiters;
+};
+
 struct Block {
     std::vector<Fiber *> fibers;
     std::vector<WarpState> warps;
     int live = 0;
     int bar_arrived = 0;
+    NamedBar named[16];
     std::vector<uint8_t> smem;
 };
 
@@ -354,6 +360,29 @@ uint32_t collective(int op, uint32_t mask, uint32_t v, uint32_t param) {
         block_current();
     }
     return f->res;
+}
+
+// bar.sync / bar.arrive on a named barrier (PTX barriers 1..15): `count` threads complete it; bar.sync blocks, bar.arrive does not
+void named_barrier(int id, int count, bool sync) {
+    Fiber *f = g_cur;
+    NamedBar &nb = f->blk->named[id & 15];
+    nb.arrived++;
+    if (nb.arrived >= count) {
+        long long mx = f->ctx.vt;
+        for (Fiber *w : nb.waiters) mx = std::max(mx, w->ctx.vt);
+        for (Fiber *w : nb.waiters) {
+            w->ctx.vt = mx + g_bar_cost;
+            push_back(w);
+        }
+        nb.waiters.clear();
+        nb.arrived = 0;
+        return;
+    }
+    if (sync) {
+        f->state = WAIT_NAMED;
+        nb.waiters.push_back(f);
+        block_current();
+    }
 }
 
 void syncthreads() {

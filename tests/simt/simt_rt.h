@@ -58,6 +58,7 @@ enum Op { OP_SYNC, OP_IDX, OP_BALLOT, OP_MATCH_ANY, OP_MAX, OP_MIN, OP_ADD, OP_O
 uint32_t collective(int op, uint32_t mask, uint32_t v, uint32_t param);
 extern int cur_site;                // source site of the collective being executed (see the macros at the end of this file)
 void syncthreads();
+void named_barrier(int id, int count, bool sync);
 void cluster_sync();
 void poll();                        // a poll point: lets other fibres run
 void cost(int cycles);              // virtual-time bookkeeping (timing model)
