@@ -500,18 +500,20 @@ extern "C" int orz_batch_run(orz_batch *b) {
         CU_TRY(cudaStreamSynchronize(b->st));
         for (int i = 0; i < b->n; i++) b->result_len[i] = tmp[i].out_pos;
         if (b->v7 && parse7_stats_enabled()) {
-            unsigned long long d[8] = {0}, c[16] = {0};
+            unsigned long long d[8] = {0}, c[24] = {0};
             for (int i = 0; i < b->n; i++) {
                 for (int k = 0; k < 8; k++) d[k] += tmp[i].dbg[k];
-                for (int k = 0; k < 16; k++) c[k] += tmp[i].dbg7[k];
+                for (int k = 0; k < 24; k++) c[k] += tmp[i].dbg7[k];
             }
             const double st = d[0] ? (double)d[0] : 1.0, wn = d[1] ? (double)d[1] : 1.0;
             fprintf(stderr,
                     "orz_b200 stage A v7: steps %llu windows %llu (%.2f steps/window) polls-not-ready %llu repairs %llu (%.4f/step: %llu records re-resolved, %llu rebuilt from HBM) "
                     "builds %llu (%.2f/step, %.0f cycles each); list lag %.1f steps / %.0f bytes; "
-                    "resolver cycles/step: total %.1f = load %.1f + walk %.1f + hand-over %.1f + repair %.1f + wait %.1f\n",
+                    "resolver cycles/step: total %.1f = team %.1f + chase %.1f + hand-over %.1f + repair %.1f + wait %.1f; verification cuts %llu; rounds ended by: block end / item cap %llu, repair %llu, record not built %llu, edge record %llu; "
+                    "latency probes (cycles): 32 dependent IMADs %.0f, 16 dependent SHFLs %.0f, 16 dependent LDS %.0f\n",
                     d[0], d[1], (double)d[0] / wn, d[2], d[3], d[3] / st, c[6], c[7], d[4], d[4] / st, d[4] ? (double)c[8] / d[4] : 0.0, c[9] / wn, c[10] / wn,
-                    c[0] / st, c[1] / st, c[2] / st, c[3] / st, c[4] / st, c[5] / st);
+                    c[0] / st, c[1] / st, c[2] / st, c[3] / st, c[4] / st, c[5] / st, c[11], c[16] + c[19], c[17], c[18], c[20], c[15] ? (double)c[12] / c[15] : 0.0,
+                    c[15] ? (double)c[13] / c[15] : 0.0, c[15] ? (double)c[14] / c[15] : 0.0);
         } else if (getenv("ORZ_B200_STATS")) {
             unsigned long long d[8] = {0};
             for (int i = 0; i < b->n; i++)

@@ -168,7 +168,7 @@ struct EncStream {
     uint32_t chunk_flags[2];    // v7, per item buffer: bit 0 = the stream ends after this chunk (lib.rs:89)
     uint32_t ctx_count_alt[kNumCtx];
     unsigned long long dbg[8]; // stage A counters: steps, executor spin iterations (own / lazy1 / lazy2 probe), builds, aborted builds
-    unsigned long long dbg7[16]; // v7: resolver cycles total, load, walk, hand-over, repair, wait; records repaired, rebuilt from HBM; builder cycles; list lag
+    unsigned long long dbg7[24]; // v7: resolver cycles total, load, walk, hand-over, repair, wait; records repaired, rebuilt from HBM; builder cycles; list lag
 };
 
 // Per-stream decoder control block (lz.rs:348-357 LZDecoder, lib.rs:99-127 loop state)

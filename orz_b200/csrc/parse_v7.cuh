@@ -396,6 +396,19 @@ struct ByteSrc7 {
         const uint32_t w0 = ring[(p >> 2) & (kInRing / 4 - 1)], w1 = ring[((p >> 2) + 1) & (kInRing / 4 - 1)];
         return __funnelshift_r(w0, w1, (p & 3u) * 8u);
     }
+    // the same for the whole warp at once (uniform a, b): lane l compares bytes 8l .. 8l+7
+    __device__ __forceinline__ int lcp_warp(uint32_t a, uint32_t b, int lane) const {
+        if (a >= lo && b >= lo && a + 264 <= hi && b + 264 <= hi) {
+            const uint32_t o = 8u * (uint32_t)lane;
+            const uint32_t d0 = ring_u32(a + o) ^ ring_u32(b + o), d1 = ring_u32(a + o + 4) ^ ring_u32(b + o + 4);
+            const int mine = d0 ? ((__ffs(d0) - 1) >> 3) : (d1 ? 4 + ((__ffs(d1) - 1) >> 3) : 8);
+            const unsigned mm = __ballot_sync(kFull, lane < kMatchMax / 8 && mine < 8);
+            if (!mm) return kMatchMax;
+            const int l = __ffs(mm) - 1;
+            return 8 * l + __shfl_sync(kFull, mine, l);
+        }
+        return lcp(a, b);
+    }
     // mem.rs:41-51 restated byte-exact: longest common prefix of [a..) and [b..), capped at 240
     __device__ __forceinline__ int lcp(uint32_t a, uint32_t b) const {
         if (a >= lo && b >= lo && a + 248 <= hi && b + 248 <= hi) { // both ranges sit in the ring
@@ -464,7 +477,7 @@ __device__ __forceinline__ bool repair_record7(ParseShared7 &shl, const Build7 &
         const uint32_t om = rs[5];
         const bool alive = om == kNone || ((bc - 1 - om) & kOrdMask) <= (uint32_t)(kRing - 1);
         const uint32_t q1 = shl.rc_pos[0], e1 = shl.rc_exp[0], o1 = shl.rc_ord[0], mx = rs[9];
-        const uint32_t l1 = (uint32_t)src.lcp(q1, y);
+        const uint32_t l1 = (uint32_t)src.lcp_warp(q1, y, lane);
         const uint32_t fmmax = B.depth0 >= 2 ? (mx & 0xffu) : 0u;
         if (alive && B.depth0 >= 1 && l1 >= (uint32_t)kMatchMin && (l1 == (uint32_t)kMatchMax || (e1 > 0 && l1 > e1) || l1 >= fmmax)) {
             const uint32_t mlen = y + l1 < B.sbuf_len ? l1 : 0u; // matcher.rs:183
@@ -630,7 +643,9 @@ __device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t base, 
     const uint32_t m = fown | (lzneed ? ((nb1 | nb2) >> 16) : 0u);
     const bool first = block0 && lane == 0;
     const uint32_t scode = (m & 2u) ? 2u : (m & 1u) ? 1u : ((!first && ((m & 4u) || rbsens)) || x >= sbuf_len) ? 4u : lane >= 30 ? 3u : 0u;
-    const uint32_t pk = scode ? (scode | 3u << 8) : ((adv + (uint32_t)lane > 32u ? 32u - (uint32_t)lane : adv) | ty << 8 | adv << 16);
+    // (a repair stop also says which of the three records are stale: bit 16 own, 17 x+1, 18 x+2)
+    const uint32_t smask = (fown & 1u) | ((nb1 >> 16) & 1u) << 1 | ((nb2 >> 16) & 1u) << 2;
+    const uint32_t pk = scode ? (scode | 3u << 8 | smask << 16) : ((adv + (uint32_t)lane > 32u ? 32u - (uint32_t)lane : adv) | ty << 8 | adv << 16);
     const uint32_t wu = ty == kTyWord ? 0xffffffffu : (ty == kTyMatch ? wmat : wlit); // lz.rs:208,233
     pk_out[lane] = pk;
     *reinterpret_cast<uint4 *>(ent_out[lane]) = make_uint4(x, ty | (lzneed ? 4u : 0u) | adv << 8 | mlen << 16 | wexp << 24, key1 | (b2 & 0xffu) << 21, key2);
@@ -708,7 +723,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
             uint32_t n_items = 0, qhead = 0;
             unsigned long long n_windows = 0, n_wait = 0, n_repair = 0, n_rep_rec = 0, n_rep_hard = 0, n_cut = 0, n_handed = 0;
             long long cyc_wait = 0, cyc_walk = 0, cyc_commit = 0, cyc_repair = 0, cyc_load = 0;
-            unsigned long long lag_steps = 0, lag_pos = 0;
+            unsigned long long n_stopc[5] = {0, 0, 0, 0, 0};
+            unsigned long long lag_steps = 0, lag_pos = 0, probe_alu = 0, probe_shfl = 0, probe_lds = 0, probe_n = 0;
             const long long t_begin = STATS ? clock64() : 0;
             const unsigned lt_mask = (1u << lane) - 1u;
             int wd_code = 0;
@@ -721,7 +737,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 // the verification below finds the first step that an earlier step of the same super-window would have changed.
                 const long long t0 = STATS ? clock64() : 0;
                 const uint32_t max_steps = items_cap - n_items < 32u ? items_cap - n_items : 32u;
-                uint32_t nst = 0, base = spos;
+                uint32_t nst = 0, base = spos, rmask = 0;
                 int stop = 0;
                 // ---- the decide team takes the decision of the next kTeam7 * 30 positions, one block per warp, all at once
                 if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&shl.team_base) = spos;
@@ -731,6 +747,29 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 bar_sync7(2, kTeamThreads);   // done: every team warp arrives at barrier 2 when its block is written
                 const long long tq = STATS ? clock64() : 0;
                 if (STATS) cyc_load += tq - t0;
+                if (STATS && (n_windows & 63u) == 0) {
+                    // latency probes of this warp under the launch's real load: 32 dependent adds, 16 dependent shuffles, 16 dependent
+                    // shared loads (pointer chase through sidx, filled with a fixed permutation of itself below)
+                    uint32_t acc = (uint32_t)lane;
+                    const long long p0 = clock64();
+#pragma unroll
+                    for (int i = 0; i < 32; i++) acc = acc * 3u + (uint32_t)i;
+                    const long long p1 = clock64();
+                    uint32_t sv = acc;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) sv = __shfl_sync(kFull, sv, (int)(sv & 31u));
+                    const long long p2 = clock64();
+                    uint32_t li = (uint32_t)lane;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) li = ld_vol_u32(&shl.lastkey[(li * 33u + 7u) & 4095u]) & 4095u;
+                    const long long p3 = clock64();
+                    probe_alu += (unsigned long long)(p1 - p0);
+                    probe_shfl += (unsigned long long)(p2 - p1);
+                    probe_lds += (unsigned long long)(p3 - p2);
+                    probe_n++;
+                    if (sv == 0xdeadbeefu && li == 0x12345u) shl.rc_pos[0] = acc; // (keeps the probes alive)
+                }
+                const long long tq2 = STATS ? clock64() : 0;
                 // ---- chase the step chain through the blocks (lz.rs:131-236): one shuffle per step, nothing else on the chain
                 uint32_t rel = 0; // position of the chase relative to spos
                 for (uint32_t t = 0, cur = 0;;) {
@@ -741,6 +780,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                         const uint32_t v = __shfl_sync(kFull, pk, cur);
                         if ((v & 0xff00u) == 0x300u) {
                             code = (int)(v & 0xffu);
+                            rmask = (v >> 16) & 7u;
                             break;
                         }
                         path |= 1u << cur;
@@ -776,7 +816,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&shl.lead_pos) = base;
                 const long long t1 = STATS ? clock64() : 0;
                 if (STATS) {
-                    cyc_walk += t1 - t0;
+                    cyc_walk += t1 - tq2;
                     n_windows++;
                 }
                 if (nst == 0 && stop == 2) { // the next step's records are not there yet
@@ -872,7 +912,10 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                     }
                 }
                 const long long t3 = STATS ? clock64() : 0;
-                if (STATS) cyc_commit += t3 - t1;
+                if (STATS) {
+                    cyc_commit += t3 - t1;
+                    n_stopc[stop < 5 ? stop : 0]++;
+                }
                 if (stop == 1 && spos < sbuf_len && n_items < items_cap) {
                     // ---- REPAIR: the record of spos (or of a lazy neighbour it needs) is stale.  Re-resolve it in place from the step
                     // log (repair_record7); a record that cannot be repaired that way is rebuilt from HBM after the committer drained.
@@ -887,17 +930,11 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                     for (uint32_t k = 0; k < 3; k++) {
                         const uint32_t y = spos + k;
                         if (y > last_pos) break;
-                        // only records that are built and stale; a record that is not there yet is left to its builder
+                        // the records the decide team found stale (one that became stale through this very hand-over shows up in the next round)
                         const uint32_t yslot = slot7<NBW>(y);
                         uint32_t *ys = shl.sum[yslot];
-                        const uint32_t have_y = bcast0(ld_vol_u32(ys));
-                        bool stale = false;
-                        if (have_y == y) {
-                            const uint32_t yw1 = ys[1], ykey = yw1 & 0x1fffffu, yordmin = ys[5], yF = ys[6];
-                            const uint32_t ybc = shl.bcnt[ykey >> 13];
-                            const uint32_t ylk = shl.lastkey[(ykey ^ (ykey >> 9)) & 4095u];
-                            stale = ylk >= yF || ((yw1 >> 27) & 1u) || (yordmin != kNone && ((ybc - 1 - yordmin) & kOrdMask) > (uint32_t)(kRing - 1));
-                        }
+                        const uint32_t have_y = y;
+                        const bool stale = (rmask >> k) & 1u;
                         if (have_y == y && stale && (k == 0 || lzneed0)) {
                             if (!repair_record7(shl, B, src, y, yslot, spos, qhead, lane)) {
                                 if (STATS) n_rep_hard++;
@@ -947,6 +984,11 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                     S->dbg7[9] += lag_steps;
                     S->dbg7[10] += lag_pos;
                     S->dbg7[11] += n_cut;
+                    S->dbg7[12] += probe_alu;
+                    S->dbg7[13] += probe_shfl;
+                    S->dbg7[14] += probe_lds;
+                    S->dbg7[15] += probe_n;
+                    for (int i = 0; i < 5; i++) S->dbg7[16 + i] += n_stopc[i];
                 }
             }
         } else if (rank == 0 && warp == 1) {
