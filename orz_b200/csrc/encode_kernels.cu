@@ -286,6 +286,18 @@ __device__ __forceinline__ uint4 lds_volatile_v4(const volatile void *p) {
     return v;
 }
 
+__device__ __forceinline__ uint2 lds_volatile_v2(const volatile void *p) {
+    uint2 v;
+#ifdef ORZ_SIMT_EMU
+    ORZ_POLL();
+    v = *reinterpret_cast<const uint2 *>(const_cast<const void *>(p));
+    return v;
+#endif
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(const_cast<void *>(p));
+    asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+
 struct ParseShared {
     uint16_t words[32768];         // lz.rs:52 — only the executor touches it
     uint32_t cnt[kNumCtx];

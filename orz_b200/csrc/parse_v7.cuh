@@ -57,7 +57,16 @@ namespace orz {
 constexpr int kListCap = 64;           // entries per key list (circular, newest at (count-1) % 64)
 constexpr int kMaxDepth7 = 48;         // deepest LZCfg depth this kernel handles (levels 0-2 use 45)
 constexpr int kRing7 = 512;            // probe record slots in CTA 0's shared memory
-constexpr uint32_t kLeadTarget7 = 128; // how far ahead of the parse records are built: every position of lead is a chance to go stale
+#ifndef ORZ_V7_LEAD
+#define ORZ_V7_LEAD 128
+#endif
+#ifndef ORZ_V7_MUT_TIGHT
+#define ORZ_V7_MUT_TIGHT 0u // (mutation hook of the A/B builds: a wrong ring-edge check must break the 100 MB identity test)
+#endif
+#ifndef ORZ_V7_TEAM
+#define ORZ_V7_TEAM 4
+#endif
+constexpr uint32_t kLeadTarget7 = ORZ_V7_LEAD; // how far ahead of the parse records are built: every position of lead is a chance to go stale
 constexpr int kExtCand = 48;           // candidates per record kept for repairs
 constexpr int kSumWords = 12;          // summary words per record
 constexpr int kExtWords = 2 + kExtCand; // F_ext, ord0, candidates
@@ -66,7 +75,7 @@ constexpr int kInRing = 4096;           // bytes of the window mirrored in CTA 0
 constexpr uint32_t kInAhead = 1536;    // ... from 2048 bytes behind the parse position to this far ahead of it
 constexpr uint32_t kOrdMask = 0x7fffffffu;
 constexpr uint32_t kTyLit = 0, kTyWord = 1, kTyMatch = 2;
-constexpr int kTeam7 = 4;              // decide warps beside the resolver: 4 x 30 positions per round
+constexpr int kTeam7 = ORZ_V7_TEAM;            // decide warps beside the resolver: 4 x 30 positions per round
 constexpr int kTeamThreads = (kTeam7 + 1) * 32; // ... and the resolver: the threads of the two round barriers
 
 // A key list entry: pos:25 | expected(low 7 bits):7  ,  ordinal:31 | expected(bit 7):1
@@ -156,7 +165,7 @@ struct ParseShared7 {
     uint32_t inring[kInRing / 4];           // window bytes around the parse position (byte p at p % 4096), kept by the feeder warp
     uint32_t rc_pos[32], rc_exp[32], rc_ord[32]; // repair scratch: recent steps with the record's key
     // the decide team: block t covers positions team_base + 30 t + lane; for every lane the chase word and the step it would take
-    uint32_t pk_all[kTeam7][32];            // advance clamped to the block | type << 8 | true advance << 16; type 3 = stop code
+    uint2 pk_all[kTeam7][32];               // the chase from this lane, resolved inside the block: x = lanes stepped on, y = where it ends (see decide_block7)
     uint32_t ent_all[kTeam7 * 32][8];       // x, type|advance|lengths, key of x+1 | literal byte, key of x+2, key, words update, hash2 | words entry read, matched ordinal
     uint32_t sidx[32];                      // the super-window's steps: index into ent_all
     uint2 vkw[32];                          // ... and their (key, words update), for the verification loop
@@ -593,7 +602,7 @@ __device__ __forceinline__ uint32_t slot7(uint32_t y) {
 // as if it were the next step, and leaves the chase word and the step's data for the resolver.  `block0`: lane 0 of this block is
 // the first step of the super-window (records that are exact only for a first step are usable there).
 template <int NBW>
-__device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t base, bool block0, uint32_t sbuf_len, int lane, uint32_t *pk_out,
+__device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t base, bool block0, uint32_t sbuf_len, int lane, uint2 *pk_out,
                                               uint32_t (*ent_out)[8]) {
     const uint32_t x = base + (uint32_t)lane;
     const uint32_t *rs = shl.sum[slot7<NBW>(x)];
@@ -640,15 +649,33 @@ __device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t base, 
     // code 1 = a record must be repaired first, 2 = a record is not built yet, 3 = next block, 4 = end of the super-window.
     // The records of x+1 / x+2 only matter if the step evaluates lazy matches; a tight record or a robitlen < 8 that an insert could
     // flip is exact only for the FIRST step of a super-window.
-    const uint32_t m = fown | (lzneed ? ((nb1 | nb2) >> 16) : 0u);
+    // (the step's own record when tight is checked exactly at verification: `room` further inserts into its bucket keep its oldest
+    // candidate alive; tight records of the lazy neighbours stay first-step-only)
+    const uint32_t m = (fown & 3u) | (lzneed ? ((nb1 | nb2) >> 16) : 0u);
+    const uint32_t room5 = room < 0 ? 0u : (room > 31 ? 31u : (uint32_t)room);
     const bool first = block0 && lane == 0;
     const uint32_t scode = (m & 2u) ? 2u : (m & 1u) ? 1u : ((!first && ((m & 4u) || rbsens)) || x >= sbuf_len) ? 4u : lane >= 30 ? 3u : 0u;
-    // (a repair stop also says which of the three records are stale: bit 16 own, 17 x+1, 18 x+2)
+    // (a repair stop also says which of the three records are stale: bit 0 own, 1 x+1, 2 x+2)
     const uint32_t smask = (fown & 1u) | ((nb1 >> 16) & 1u) << 1 | ((nb2 >> 16) & 1u) << 2;
-    const uint32_t pk = scode ? (scode | 3u << 8 | smask << 16) : ((adv + (uint32_t)lane > 32u ? 32u - (uint32_t)lane : adv) | ty << 8 | adv << 16);
+    // The chase of the step chain through this block, from every lane at once (pointer doubling, 5 rounds cover 32 hops): a step lane
+    // points at lane + advance, a stop lane at itself.  Afterwards lane l knows the lanes a chase entering at l steps on and where it
+    // ends: a position past the block (>= 32, the true advance of the last step) or the stop lane it runs into.
+    uint32_t nxt = scode ? (uint32_t)lane : (uint32_t)lane + adv;
+    uint32_t msk = scode ? 0u : 1u << lane;
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const uint32_t m2 = __shfl_sync(kFull, msk, (int)(nxt & 31u)), n2 = __shfl_sync(kFull, nxt, (int)(nxt & 31u));
+        if (nxt < 32u) {
+            msk |= m2;
+            nxt = n2;
+        }
+    }
+    const uint32_t sinfo = __shfl_sync(kFull, scode | smask << 4, (int)(nxt & 31u));
+    // x = lanes stepped on; y = end (lane or position relative to the block) | stop code << 12 | stale mask << 16
+    const uint2 pk = make_uint2(msk, nxt | (nxt < 32u ? sinfo << 12 : 0u));
     const uint32_t wu = ty == kTyWord ? 0xffffffffu : (ty == kTyMatch ? wmat : wlit); // lz.rs:208,233
     pk_out[lane] = pk;
-    *reinterpret_cast<uint4 *>(ent_out[lane]) = make_uint4(x, ty | (lzneed ? 4u : 0u) | adv << 8 | mlen << 16 | wexp << 24, key1 | (b2 & 0xffu) << 21, key2);
+    *reinterpret_cast<uint4 *>(ent_out[lane]) = make_uint4(x, ty | (lzneed ? 4u : 0u) | room5 << 3 | adv << 8 | mlen << 16 | wexp << 24, key1 | (b2 & 0xffu) << 21, key2);
     *reinterpret_cast<uint4 *>(ent_out[lane] + 4) = make_uint4(key, wu, h2 | lwe << 15, word);
 }
 
@@ -773,21 +800,9 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 // ---- chase the step chain through the blocks (lz.rs:131-236): one shuffle per step, nothing else on the chain
                 uint32_t rel = 0; // position of the chase relative to spos
                 for (uint32_t t = 0, cur = 0;;) {
-                    const uint32_t pk = ld_vol_u32(&shl.pk_all[t][lane]);
-                    uint32_t path = 0, vlast = 0;
-                    int code = 0;
-                    for (;;) {
-                        const uint32_t v = __shfl_sync(kFull, pk, cur);
-                        if ((v & 0xff00u) == 0x300u) {
-                            code = (int)(v & 0xffu);
-                            rmask = (v >> 16) & 7u;
-                            break;
-                        }
-                        path |= 1u << cur;
-                        vlast = v;
-                        cur += v & 0xffu;
-                        if (cur & 32u) break;
-                    }
+                    const uint2 pv = lds_volatile_v2(&shl.pk_all[t][cur]); // (one broadcast load: the team chased the block from every lane)
+                    uint32_t path = pv.x;
+                    int code = (int)((pv.y >> 12) & 0xfu);
                     uint32_t np = (uint32_t)__popc(path);
                     if (nst + np > max_steps) { // keep only the steps that still fit (the chunk's item limit, lz.rs:131, or 32)
                         uint32_t keep = path;
@@ -796,8 +811,9 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                         path = keep;
                         np = (uint32_t)__popc(path);
                         code = 4;
-                    } else if (np > 0 && (cur & 32u)) { // the last step leaves the block: its true advance (the chase value was clamped)
-                        cur = (uint32_t)(31 - __clz(path)) + ((vlast >> 16) & 0xffu);
+                    } else {
+                        cur = pv.y & 0xfffu; // the stop lane, or the position past the block the last step lands on
+                        rmask = (pv.y >> 16) & 7u;
                     }
                     if ((path >> lane) & 1u) shl.sidx[nst + (uint32_t)__popc(path & lt_mask)] = t * 32u + (uint32_t)lane;
                     nst += np;
@@ -847,20 +863,28 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                         shl.vkw[lane] = make_uint2(e1.x, e1.y);
                     }
                     __syncwarp();
-                    const uint32_t x = e0.x, ty = e0.y & 3u, lzn = (e0.y >> 2) & 1u, adv = (e0.y >> 8) & 0xffu, mlen = (e0.y >> 16) & 0xffu, wexp = e0.y >> 24;
+                    const uint32_t x = e0.x, ty = e0.y & 3u, lzn = (e0.y >> 2) & 1u, room5 = (e0.y >> 3) & 31u, adv = (e0.y >> 8) & 0xffu, mlen = (e0.y >> 16) & 0xffu, wexp = e0.y >> 24;
                     const uint32_t key = e1.x, key1 = e0.z & 0x1fffffu, key2 = e0.w, wu = e1.y, h2 = e1.z & 0x7fffu, lwe = e1.z >> 15, word = e1.w;
                     const uint32_t b2lo = e0.z >> 21;
-                    bool viol = false;
+                    // earlier steps of the super-window that insert into this step's bucket: more than `room` of them and the oldest
+                    // candidate of its record has left the ring (matcher.rs:82-87) by the time the step is taken
+                    const unsigned mb = __match_any_sync(kFull, live ? key >> 13 : 256u + (uint32_t)lane);
+                    bool viol = (uint32_t)__popc(mb & lt_mask) > room5 + ORZ_V7_MUT_TIGHT;
                     uint32_t wnext = 32; // the next step of the super-window that writes the same words entry (the last writer wins)
-                    for (uint32_t j = 0; j < nst; j++) {
-                        const uint2 kw = shl.vkw[j]; // (one broadcast load)
-                        const uint32_t kj = kw.x, wj = kw.y;
-                        const uint32_t wi = wj & 0x7fffu;
-                        if (j < (uint32_t)lane) {
+                    // (four steps per trip, their broadcast loads issued together: a lone warp pays the full shared-memory latency otherwise)
+                    for (uint32_t j0 = 0; j0 < nst; j0 += 4) {
+                        uint2 kw4[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) kw4[u] = shl.vkw[(j0 + (uint32_t)u) & 31u];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t j = j0 + (uint32_t)u;
+                            const uint32_t kj = kw4[u].x, wj = kw4[u].y;
+                            const uint32_t wi = wj & 0x7fffu;
                             // an earlier step put a node on one of the lists this step read, or changed the words entry it read
-                            viol = viol || kj == key || (lzn && (kj == key1 || kj == key2)) || (wj != 0xffffffffu && wi == h2 && (wj >> 15) != lwe);
-                        } else if (j > (uint32_t)lane && wnext == 32u && wj != 0xffffffffu && wu != 0xffffffffu && wi == (wu & 0x7fffu)) {
-                            wnext = j;
+                            const bool hit = kj == key || (lzn && (kj == key1 || kj == key2)) || (wj != 0xffffffffu && wi == h2 && (wj >> 15) != lwe);
+                            viol = viol || (j < (uint32_t)lane && j < nst && hit);
+                            if (j > (uint32_t)lane && j < nst && wnext == 32u && wj != 0xffffffffu && wu != 0xffffffffu && wi == (wu & 0x7fffu)) wnext = j;
                         }
                     }
                     const unsigned vm = __ballot_sync(kFull, viol && live);
