@@ -507,11 +507,11 @@ extern "C" int orz_batch_run(orz_batch *b) {
             }
             const double st = d[0] ? (double)d[0] : 1.0, wn = d[1] ? (double)d[1] : 1.0;
             fprintf(stderr,
-                    "orz_b200 stage A v7: steps %llu windows %llu (%.2f steps/window) polls-not-ready %llu repairs %llu (%.4f/step: %llu records re-resolved, %llu rebuilt from HBM) "
-                    "builds %llu (%.2f/step, %.0f cycles each); list lag %.1f steps / %.0f bytes; "
+                    "orz_b200 stage A v7: steps %llu windows %llu (%.2f steps/window) polls-not-ready %llu repairs %llu (%.4f/step: %llu records re-resolved — %llu alias, %llu one newer node, %llu in full — %llu rebuilt from HBM) "
+                    "builds %llu (%.2f/step, %.0f cycles each), refreshes %llu (parse waited for one %llu times); list lag %.1f steps / %.0f bytes; "
                     "resolver cycles/step: total %.1f = team %.1f + chase %.1f + hand-over %.1f + repair %.1f + wait %.1f; verification cuts %llu; rounds ended by: block end / item cap %llu, repair %llu, record not built %llu, edge record %llu; "
                     "latency probes (cycles): 32 dependent IMADs %.0f, 16 dependent SHFLs %.0f, 16 dependent LDS %.0f\n",
-                    d[0], d[1], (double)d[0] / wn, d[2], d[3], d[3] / st, c[6], c[7], d[4], d[4] / st, d[4] ? (double)c[8] / d[4] : 0.0, c[9] / wn, c[10] / wn,
+                    d[0], d[1], (double)d[0] / wn, d[2], d[3], d[3] / st, c[6], c[21], c[22], c[23], c[7], d[4], d[4] / st, d[4] ? (double)c[8] / d[4] : 0.0, d[5], d[6], c[9] / wn, c[10] / wn,
                     c[0] / st, c[1] / st, c[2] / st, c[3] / st, c[4] / st, c[5] / st, c[11], c[16] + c[19], c[17], c[18], c[20], c[15] ? (double)c[12] / c[15] : 0.0,
                     c[15] ? (double)c[13] / c[15] : 0.0, c[15] ? (double)c[14] / c[15] : 0.0);
         } else if (getenv("ORZ_B200_STATS")) {

@@ -29,31 +29,60 @@ struct DecShared {
     uint16_t bhead[kNumBuckets];
     uint16_t vs[kSymStride + 8];
     uint32_t num_counted;
-    int16_t ctag[128];   // rank-table cache tags (context id, -1 = empty)
+    int16_t ctag[128];   // rank-table cache tags (context id, -1 = empty): set s holds slots 2s and 2s+1
+    uint8_t clru[64];    // per set: the way to replace next (the one not used last)
 };
 
-// Direct-mapped, write-back cache of rank tables in shared memory (few-stream launches: one block per SM).
-// Every item reads and writes its context's table; in global memory each store evicts the line from L1, so the
-// four dependent loads of symrank.rs:49-97 each cost an L2 round trip.  Called by the whole warp in lock step.
+// Two-way set-associative, write-back cache of rank tables in shared memory (few-stream launches: one block per SM).
+// Every item reads and writes its context's table (symrank.rs:49-97: three dependent loads); in global memory each of them is an
+// L2 round trip, because the item's own stores keep evicting the lines from L1.  A miss swaps 1576 bytes: the fill is issued first
+// (independent loads, one L2 latency), the victim is written back while it is in flight.  Called by the whole warp in lock step.
 template <int CACHE>
-__device__ __forceinline__ SymRank *rank_table(SymRank *symranks, SymRank *cache, int16_t *ctag, uint32_t ctx, unsigned &misses) {
+__device__ __forceinline__ SymRank *rank_table(SymRank *symranks, SymRank *cache, DecShared &sh, uint32_t ctx, unsigned &misses) {
     if (CACHE == 0) return &symranks[ctx];
-    const uint32_t slot = ((ctx & 0x7fu) + 43u * (ctx >> 7)) & (uint32_t)(CACHE - 1);
-    const int tag = ctag[slot];
-    if (tag != (int)ctx) { // warp-cooperative swap: 394 words out, 394 words in
-        misses++;
-        const int lane = threadIdx.x & 31;
-        uint32_t *c32 = reinterpret_cast<uint32_t *>(&cache[slot]);
-        if (tag >= 0) {
-            uint32_t *g32 = reinterpret_cast<uint32_t *>(&symranks[tag]);
-            for (int i = lane; i < (int)(sizeof(SymRank) / 4); i += 32) g32[i] = c32[i];
-        }
-        __syncwarp();
-        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(&symranks[ctx]);
-        for (int i = lane; i < (int)(sizeof(SymRank) / 4); i += 32) c32[i] = s32[i];
-        ctag[slot] = (int16_t)ctx;
-        __syncwarp();
+    constexpr uint32_t kSets = CACHE / 2;
+    const uint32_t set = ctx % kSets;
+    const int t0 = sh.ctag[2 * set], t1 = sh.ctag[2 * set + 1];
+    if (t0 == (int)ctx) {
+        sh.clru[set] = 1;
+        return &cache[2 * set];
     }
+    if (t1 == (int)ctx) {
+        sh.clru[set] = 0;
+        return &cache[2 * set + 1];
+    }
+    misses++;
+    const int lane = threadIdx.x & 31;
+    const uint32_t way = sh.clru[set], slot = 2 * set + way;
+    const int tag = way ? t1 : t0;
+    constexpr int kW = (int)(sizeof(SymRank) / 8); // 197 eight-byte words
+    constexpr int kR = (kW + 31) / 32;
+    uint2 *c64 = reinterpret_cast<uint2 *>(&cache[slot]);
+    const uint2 *s64 = reinterpret_cast<const uint2 *>(&symranks[ctx]);
+    uint2 fill[kR];
+#pragma unroll
+    for (int j = 0; j < kR; j++) {
+        const int i = lane + 32 * j;
+        fill[j] = i < kW ? ldcg_u2(&s64[i]) : make_uint2(0, 0);
+    }
+    __syncwarp();
+    if (tag >= 0) {
+        uint2 *g64 = reinterpret_cast<uint2 *>(&symranks[tag]);
+#pragma unroll
+        for (int j = 0; j < kR; j++) {
+            const int i = lane + 32 * j;
+            if (i < kW) g64[i] = c64[i];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kR; j++) {
+        const int i = lane + 32 * j;
+        if (i < kW) c64[i] = fill[j];
+    }
+    sh.ctag[slot] = (int16_t)ctx;
+    sh.clru[set] = (uint8_t)(way ^ 1u);
+    __syncwarp();
     return &cache[slot];
 }
 
@@ -207,13 +236,18 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
     if (S->status != 0) return;
     ORZ_DYN_SHARED(smem_raw);
     DecShared &sh = *reinterpret_cast<DecShared *>(smem_raw);
-    SymRank *cache = reinterpret_cast<SymRank *>(smem_raw + ((sizeof(DecShared) + 15) & ~size_t(15)));
+    // on-chip mode (CACHE > 0): the words table (lz.rs:52) and CACHE rank tables live in shared memory
+    uint16_t *wsm = reinterpret_cast<uint16_t *>(smem_raw + ((sizeof(DecShared) + 15) & ~size_t(15)));
+    SymRank *cache = reinterpret_cast<SymRank *>(smem_raw + ((sizeof(DecShared) + 15) & ~size_t(15)) + (CACHE ? 65536 : 0));
     const int lane = threadIdx.x;
 
     for (int i = lane; i < kNumBuckets; i += 32) sh.bhead[i] = (uint16_t)S->bhead[i];
     for (int i = lane; i < 128; i += 32) sh.ctag[i] = -1;
+    for (int i = lane; i < 64; i += 32) sh.clru[i] = 0;
     Node *nodes = S->nodes;
-    uint16_t *words = S->words;
+    if (CACHE)
+        for (int i = lane; i < 32768 / 8; i += 32) reinterpret_cast<uint4 *>(wsm)[i] = reinterpret_cast<const uint4 *>(S->words)[i];
+    uint16_t *words = CACHE ? wsm : S->words;
     SymRank *symranks = S->symranks;
     const bool self_driven = S->self_driven != 0;
     const uint8_t *in = S->in;
@@ -353,7 +387,7 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
                 const uint32_t c = (b_m1 & 0x7fu) | is_alnum(b_m2) << 7;
                 const uint32_t h2 = (b_m1 & 0x7fu) | ((b_m2 & 0x7fu) | is_alnum(b_m3) << 7) << 7;
                 const uint32_t lwe = words[h2];
-                SymRank *sr = rank_table<CACHE>(symranks, cache, sh.ctag, c | after_literal << 8, misses);
+                SymRank *sr = rank_table<CACHE>(symranks, cache, sh, c | after_literal << 8, misses);
                 const uint32_t ecnt0 = sr->cnt, esum0 = sr->sum; // issued early: independent of the bit stream
                 const uint32_t iun = sr->index[lwe & 0xffu];
                 const int sym = decode_sym(br, sh.h[after_literal]);
@@ -455,7 +489,36 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
                     // hashes are carried in registers: a load right after a store to the same line misses L1.
                     const uint32_t dist = spos - mpos;
                     uint32_t y5;
-                    if (dist >= 4) {
+                    if (dist >= mlen && mlen <= 256u) {
+                        // source and destination do not overlap: the whole copy in one round trip, lane l moves bytes 8l .. 8l+7
+                        const uint32_t off = 8u * (uint32_t)lane;
+                        uint32_t lo = 0, hi = 0;
+                        if (off < mlen) {
+                            lo = ld_u32_unaligned(wa, mpos + off + dl);
+                            if (off + 4 < mlen) hi = ld_u32_unaligned(wa, mpos + off + 4 + dl);
+                            const uint32_t nb = mlen - off; // bytes of this lane (>= 1)
+                            uint8_t *d = win + spos + off;
+                            d[0] = (uint8_t)lo;
+                            if (nb > 1) d[1] = (uint8_t)(lo >> 8);
+                            if (nb > 2) d[2] = (uint8_t)(lo >> 16);
+                            if (nb > 3) d[3] = (uint8_t)(lo >> 24);
+                            if (nb > 4) d[4] = (uint8_t)hi;
+                            if (nb > 5) d[5] = (uint8_t)(hi >> 8);
+                            if (nb > 6) d[6] = (uint8_t)(hi >> 16);
+                            if (nb > 7) d[7] = (uint8_t)(hi >> 24);
+                        }
+                        // the five bytes before the new position (for the next hashes): they sit in lane A and the lane before it
+                        // (or in prev4 when A == 0); positions 8A-8 .. 8A+7 of the match as one 128-bit value, bytes idx-4 .. idx wanted
+                        const uint32_t A = (mlen - 1) >> 3;
+                        const uint32_t alo = __shfl_sync(0xffffffffu, lo, (int)A), ahi = __shfl_sync(0xffffffffu, hi, (int)A);
+                        const uint32_t plo = __shfl_sync(0xffffffffu, lo, (int)(A ? A - 1 : 0)), phi = __shfl_sync(0xffffffffu, hi, (int)(A ? A - 1 : 0));
+                        const unsigned long long vA = (unsigned long long)ahi << 32 | alo;
+                        const unsigned long long vP = A ? ((unsigned long long)phi << 32 | plo) : ((unsigned long long)prev4 << 32);
+                        const uint32_t sh8 = (mlen - 1 - 8u * A + 4u) * 8u; // (idx - 4) * 8 with idx = mlen - 1 - 8A + 8: 32 .. 88
+                        const unsigned long long x5 = sh8 < 64u ? (vP >> sh8) | (vA << (64u - sh8)) : (vA >> (sh8 - 64u));
+                        y5 = (uint32_t)x5 & 0xffu;
+                        prev4 = (uint32_t)(x5 >> 8);
+                    } else if (dist >= 4) {
                         uint32_t lo = prev4, hi = 0, left = 0;
                         for (uint32_t q = 0; q < mlen; q += 4) {
                             const uint32_t wv = ld_u32_unaligned(wa, mpos + q + dl);
@@ -529,7 +592,8 @@ __global__ void __launch_bounds__(32) orz_decode_kernel(DecStream *streams) {
     }
 
     __syncwarp();
-    if (CACHE > 0) { // write the cached rank tables back (the state persists across chunk-mode calls)
+    if (CACHE > 0) { // write the words table and the cached rank tables back (the state persists across chunk-mode calls)
+        for (int i = lane; i < 32768 / 8; i += 32) reinterpret_cast<uint4 *>(S->words)[i] = reinterpret_cast<const uint4 *>(wsm)[i];
         for (int sl = 0; sl < CACHE; sl++) {
             const int tag = sh.ctag[sl];
             if (tag < 0) continue;
@@ -566,20 +630,20 @@ __global__ void __launch_bounds__(256) orz_dec_forward_kernel(DecStream *streams
     }
 }
 
+constexpr int kDecCache = 94; // rank tables cached per stream in on-chip mode: 47 sets x 2 ways beside the 64 KB words table
 void launch_decode(DecStream *d_streams, int n, cudaStream_t st) {
     constexpr size_t base = (sizeof(DecShared) + 15) & ~size_t(15);
-    constexpr size_t big = base + 128 * sizeof(SymRank);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(orz_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big);
-        cudaFuncSetAttribute(orz_decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
-        attr_set = true;
-    }
-    // few streams: one block per SM with 128 rank tables cached in shared memory; many streams: several blocks per SM
-    const char *force = getenv("ORZ_B200_DEC_CACHE");
-    // measured in round 1: the cache does not pay (misses ~17 % of items, a swap costs as much as it saves): off by default
-    const bool cached = force ? atoi(force) != 0 : false;
-    if (cached) ORZ_LAUNCH(orz_decode_kernel<128>, n, 32, big, st, d_streams);
+    constexpr size_t big = base + 65536 + kDecCache * sizeof(SymRank);
+    static_assert(big <= 232448, "decoder: shared memory of the on-chip mode");
+    // (attributes are per device: set on every launch, it is a cheap call)
+    cudaFuncSetAttribute(orz_decode_kernel<kDecCache>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big);
+    cudaFuncSetAttribute(orz_decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
+    // few streams (at most two per SM's worth of waves): one block per SM with the words table and 94 rank tables in shared memory,
+    // the item chain runs out of on-chip memory.  Many streams: several blocks per SM hide each other's L2 latency instead.
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 2 * sms) ORZ_LAUNCH(orz_decode_kernel<kDecCache>, n, 32, big, st, d_streams);
     else ORZ_LAUNCH(orz_decode_kernel<0>, n, 32, base, st, d_streams);
 }
 void launch_dec_forward(DecStream *d_stream, uint32_t forward_len, cudaStream_t st) {

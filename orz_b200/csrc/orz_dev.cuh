@@ -201,6 +201,14 @@ __device__ __forceinline__ uint32_t hash_dword(uint32_t v) {
     return ((v & 0xffu) * 131313131u ^ 797u) + (((v >> 8) & 0xffu) * 1313131u ^ 79797u) +
            (((v >> 16) & 0xffu) * 13131u ^ 7979797u) + ((v >> 24) * 131u ^ 797979797u);
 }
+// L2-only load (bypasses L1: coherent with stores of any SM)
+__device__ __forceinline__ uint2 ldcg_u2(const uint2 *p) {
+#ifdef ORZ_SIMT_EMU
+    return *p;
+#else
+    return __ldcg(p);
+#endif
+}
 // unaligned little-endian dword from a 4-byte-aligned base (global or shared)
 __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *base, uint32_t off) {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(base + (off & ~3u));

@@ -43,6 +43,7 @@
 #endif
 
 #ifdef ORZ_SIMT_EMU
+#include <cstddef>
 #include <cstdio>
 #define V7_TRACE(...)                                              \
     do {                                                           \
@@ -58,10 +59,13 @@ constexpr int kListCap = 64;           // entries per key list (circular, newest
 constexpr int kMaxDepth7 = 48;         // deepest LZCfg depth this kernel handles (levels 0-2 use 45)
 constexpr int kRing7 = 512;            // probe record slots in CTA 0's shared memory
 #ifndef ORZ_V7_LEAD
-#define ORZ_V7_LEAD 128
+#define ORZ_V7_LEAD 96
 #endif
 #ifndef ORZ_V7_MUT_TIGHT
 #define ORZ_V7_MUT_TIGHT 0u // (mutation hook of the A/B builds: a wrong ring-edge check must break the 100 MB identity test)
+#endif
+#ifndef ORZ_V7_REFRESH
+#define ORZ_V7_REFRESH 45 // a stale record at least this far ahead of the round's base is handed back to its builder
 #endif
 #ifndef ORZ_V7_TEAM
 #define ORZ_V7_TEAM 4
@@ -75,6 +79,7 @@ constexpr int kInRing = 4096;           // bytes of the window mirrored in CTA 0
 constexpr uint32_t kInAhead = 1536;    // ... from 2048 bytes behind the parse position to this far ahead of it
 constexpr uint32_t kOrdMask = 0x7fffffffu;
 constexpr uint32_t kTyLit = 0, kTyWord = 1, kTyMatch = 2;
+constexpr uint32_t kRefreshAhead = ORZ_V7_REFRESH;
 constexpr int kTeam7 = ORZ_V7_TEAM;            // decide warps beside the resolver: 4 x 30 positions per round
 constexpr int kTeamThreads = (kTeam7 + 1) * 32; // ... and the resolver: the threads of the two round barriers
 
@@ -115,6 +120,17 @@ __device__ __forceinline__ void bar_arrive7(int id, int nthreads) {
 #endif
 }
 
+// one 16-byte volatile load through a generic address (CTA 0's shared memory seen from any CTA of the cluster)
+__device__ __forceinline__ uint4 ld_volatile_v4_generic(const void *p) {
+    uint4 v;
+#ifdef ORZ_SIMT_EMU
+    ORZ_POLL();
+    v = *reinterpret_cast<const uint4 *>(p);
+#else
+    asm volatile("ld.volatile.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+#endif
+    return v;
+}
 // cluster-scope acquire / release on generic addresses (CTA 0's shared memory seen from any CTA of the cluster)
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
 #ifdef ORZ_SIMT_EMU
@@ -130,13 +146,6 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
     *p = v;
 #else
     asm volatile("st.release.cluster.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-#endif
-}
-__device__ __forceinline__ uint2 ldcg_u2(const uint2 *p) {
-#ifdef ORZ_SIMT_EMU
-    return *p;
-#else
-    return __ldcg(p);
 #endif
 }
 __device__ __forceinline__ uint32_t ldcg_u32(const uint32_t *p) {
@@ -170,20 +179,27 @@ struct ParseShared7 {
     uint32_t sidx[32];                      // the super-window's steps: index into ent_all
     uint2 vkw[32];                          // ... and their (key, words update), for the verification loop
     uint32_t lcnt[kNumBuckets], icnt[kNumBuckets]; // the committers' own insert counts (they number the inserts of a batch in order)
+    // the four words a builder polls, in one 16-byte line: one remote (DSMEM) load per poll instead of four
     uint32_t spos;                          // parse position: every step before it is decided for good (resolver -> builders)
     uint32_t lead_pos;                      // how far the resolver has looked (>= spos; a verification cut may fall back behind it)
     uint32_t fpos;                          // every step at a position < fpos is committed to HBM (committer -> builders)
+    uint32_t done;
     uint32_t qhead;                         // steps queued (resolver)
     uint32_t qdone;                         // steps whose list entries are committed (list committer)
     uint32_t qitem;                         // steps whose items are written (item committer)
-    uint32_t done;
     uint32_t fed_hi;                        // inring holds window bytes [max(fed_lo0, fed_hi - 4096), fed_hi)
     uint32_t fed_lo0;
     uint32_t team_base;                     // first position of the decide team's round (the rounds are paced by named barriers 1 and 2)
+    // refresh of records that went stale well ahead of the parse (bit = record slot): the decide team asks (`req`), the builder that
+    // owns the slot rebuilds the record against the present frontier (`busy` while it does)
+    uint32_t req[kRing7 / 32];
+    uint32_t busy[kRing7 / 32];
 };
 
+static_assert(offsetof(ParseShared7, spos) % 16 == 0, "stage A v7: the polled line");
+
 // summary words
-//  0  stamp: the position the record describes (written last, with release semantics)
+//  0  stamp: the position the record describes | generation << 25 (a rebuild bumps it); written last, with release semantics
 //  1  key = c << 13 | e   | ncand << 21 (candidates considered, <= 48) | flags << 27 (bit 0: incomplete, must be rebuilt)
 //  2  hash2(y-1) | bytes(y, y+1) << 15
 //  3  fm_len | lazy max over depth1 << 8 | lazy max over depth2 << 16 | expected of the matched node << 24
@@ -249,8 +265,11 @@ struct Build7 {
 // Builds the record of position y against the state committed below frontier F.  `gc` = a lower bound of the bucket's
 // insert count at the time y is decided.  Writes summary + ext through `sum`/`ext` (local or DSMEM pointers) and
 // publishes the stamp last.  Warp-cooperative.
+// `mode`: 0 = first build of y in this slot; 1 = the owner rebuilds the record in place while the decide team may be reading it: the stamp
+// is taken away first and comes back with the next generation (a reader compares the stamp before and after its reads); 2 = rebuild
+// by the resolver itself (no reader is running: same generation).
 __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint32_t F, const volatile uint32_t *bcnt_src, uint32_t *sum,
-                                              uint32_t *ext, uint32_t slot, int lane) {
+                                              uint32_t *ext, uint32_t slot, int lane, int mode = 0) {
     const uint8_t *win = B.win;
     const uint32_t prev4 = ld_u32_unaligned(win, y - 4); // bytes y-4 .. y-1
     const uint32_t cur4 = ld_u32_unaligned(win, y);      // bytes y .. y+3
@@ -363,6 +382,17 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
     }
     ORZ_COST(200);
     // ---- publish: ext (all lanes), summary words 1.. (lane 0), fence, stamp
+    uint32_t stampv = y;
+    if (mode) {
+        const uint32_t cur = bcast0(ld_vol_u32(&sum[0]));
+        const uint32_t gen = (cur & 0x1ffffffu) == y ? cur >> 25 : 0u;
+        stampv = y | ((gen + (mode == 1 ? 1u : 0u)) & 0x7fu) << 25;
+        if (mode == 1) {
+            if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sum[0]) = kNone;
+            __threadfence(); // the stamp is gone before any word of the record changes
+            __syncwarp();
+        }
+    }
     if (ok0) ext[2 + lane] = (uint32_t)lcp0 | kentry_exp(en) << 8 | ((ord0 - kentry_ord(en)) & 0xfffu) << 16;
     if (ok1 && 32 + lane < kExtCand) ext[2 + 32 + lane] = (uint32_t)lcp1 | kentry_exp(en1) << 8 | ((ord0 - kentry_ord(en1)) & 0xfffu) << 16;
     uint32_t *gx = B.gext + (size_t)slot * kExtCand;
@@ -385,7 +415,7 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
     }
     // the barrier orders every lane's stores before lane 0's release store of the stamp (cumulative: no fence per lane)
     __syncwarp();
-    if (lane == 0) st_release_u32(&sum[0], y);
+    if (lane == 0) st_release_u32(&sum[0], stampv);
 }
 
 // Window bytes for repairs: from the shared-memory ring where it is guaranteed stable (the feeder only moves when the parse
@@ -435,13 +465,14 @@ struct ByteSrc7 {
 // may have been decided (they sit in the step log, committed or not), and candidates may have left the ring.  The exact candidate
 // sequence at decision time T is  [steps in [F_ext, T) with y's key, newest first]  followed by  [the record's own candidates that
 // are still alive]; matcher.rs:135-228 is re-resolved over that sequence and the summary rewritten with frontier T.
-// Returns false if the record has to be rebuilt from HBM instead (incomplete record, log does not reach back to F_ext, > 32 recent steps).
-__device__ __forceinline__ bool repair_record7(ParseShared7 &shl, const Build7 &B, const ByteSrc7 &src, uint32_t y, uint32_t slot, uint32_t T,
+// Returns 0 if the record has to be rebuilt from HBM instead (incomplete record, log does not reach back to F_ext, > 32 recent steps),
+// else how it was repaired: 1 = nothing to do (the key-hash table aliased), 2 = one newer node took the first place, 3 = re-resolved.
+__device__ __forceinline__ int repair_record7(ParseShared7 &shl, const Build7 &B, const ByteSrc7 &src, uint32_t y, uint32_t slot, uint32_t T,
                                                uint32_t qhead, int lane) {
     uint32_t *rs = shl.sum[slot];
     const uint32_t *ex = shl.ext[slot];
     const uint32_t w1 = rs[1];
-    if ((w1 >> 27) & 1u) return false;
+    if ((w1 >> 27) & 1u) return 0;
     const uint32_t key = w1 & 0x1fffffu, nold = (w1 >> 21) & 0x3fu, c = key >> 13;
     const uint32_t F_ext = ex[0], ord0 = ex[1];
     const uint32_t bc = shl.bcnt[c];
@@ -468,14 +499,14 @@ __device__ __forceinline__ bool repair_record7(ParseShared7 &shl, const Build7 &
         newer_c += (uint32_t)__popc(cm);
         if (__ballot_sync(kFull, !inrange)) reached = true;
     }
-    if (!reached || k > 32u) return false;
+    if (!reached || k > 32u) return 0;
     if (k == 0) { // the key-hash table aliased: nothing decided since F_ext has this key
         const uint32_t om = rs[5];
         if (om == kNone || ((bc - 1 - om) & kOrdMask) <= (uint32_t)(kRing - 1)) {
             __syncwarp();
             if (lane == 0) rs[6] = T;
             __syncwarp();
-            return true;
+            return 1;
         }
     }
     __syncwarp();
@@ -508,7 +539,7 @@ __device__ __forceinline__ bool repair_record7(ParseShared7 &shl, const Build7 &
                 rs[8] = hw_m | wv_m << 15;
             }
             __syncwarp();
-            return true;
+            return 2;
         }
     }
     // ---- 2. merged candidate sequence, 32 per round: lanes < k hold the recent steps (round 0), the others the record's candidates
@@ -586,7 +617,7 @@ __device__ __forceinline__ bool repair_record7(ParseShared7 &shl, const Build7 &
         rs[8] = hw_m | wv_m << 15;
     }
     __syncwarp();
-    return true;
+    return 3;
 }
 
 // Record slots are private to builders: builder b = y % NBW owns SL = 512 / NBW slots and is the only writer of the record of y,
@@ -602,7 +633,7 @@ __device__ __forceinline__ uint32_t slot7(uint32_t y) {
 // as if it were the next step, and leaves the chase word and the step's data for the resolver.  `block0`: lane 0 of this block is
 // the first step of the super-window (records that are exact only for a first step are usable there).
 template <int NBW>
-__device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t base, bool block0, uint32_t sbuf_len, int lane, uint2 *pk_out,
+__device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t round_base, uint32_t base, bool block0, uint32_t sbuf_len, int lane, uint2 *pk_out,
                                               uint32_t (*ent_out)[8]) {
     const uint32_t x = base + (uint32_t)lane;
     const uint32_t *rs = shl.sum[slot7<NBW>(x)];
@@ -611,7 +642,8 @@ __device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t base, 
     const uint4 a = lds_volatile_v4(rs);
     const uint4 b = lds_volatile_v4(rs + 4);
     const uint32_t wmat = ld_vol_u32(rs + 8);
-    const bool ready = a.x == x;
+    const uint32_t stamp2 = ld_vol_u32(rs); // (a rebuild in place takes the stamp away first and returns it with another generation)
+    const bool ready = (a.x & 0x1ffffffu) == x && a.x == stamp2;
     const uint32_t key = a.y & 0x1fffffu, c = key >> 13;
     const bool incomplete = (a.y >> 27) & 1u;
     const uint32_t h2 = a.z & 0x7fffu, b2 = a.z >> 15;
@@ -622,13 +654,20 @@ __device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t base, 
     const uint32_t kh = (key ^ (key >> 9)) & 4095u;
     const uint32_t lk = ld_vol_u32(&shl.lastkey[kh]);
     // exactness of the record at decision time (see the header): no step with this key since F, oldest candidate alive.
-    // `tight`: fewer than 32 further inserts keep the oldest candidate alive — exact only for the super-window's first step.
-    // flag bits: 1 = stale (repair), 2 = not built yet, 4 = tight.  (Branch-free on purpose: a warp that is alone on its SM
+    // `room`: this many further inserts into the bucket keep the record's oldest candidate alive (checked at verification).
+    // flag bits: 1 = stale (repair), 2 = not built yet.  (Branch-free on purpose: a warp that is alone on its SM
     // sub-partition pays a pipeline refill for every divergent branch.)
     const int room = ordmin == kNone ? 64 : (int)(kRing - 1) - (int)((bc - 1 - ordmin) & kOrdMask);
-    const uint32_t fown = !ready ? 2u : (((lk >= F || incomplete || room < 0) ? 1u : 0u) | (room < 32 ? 4u : 0u));
+    const uint32_t fown = !ready ? 2u : ((lk >= F || incomplete || room < 0) ? 1u : 0u);
+    // a stale record far enough ahead is handed back to its builder: rebuilt against the present frontier it is exact again by the
+    // time the parse gets there (if the step that made it stale is below the frontier by now; the parse repairs the near ones itself)
+    if (ready && (fown & 1u) && x >= round_base + kRefreshAhead && x <= sbuf_len + 1u && (incomplete || room < 0 || lk < ld_vol_u32(&shl.fpos))) {
+        const uint32_t slot = slot7<NBW>(x), w = slot >> 5, bit = 1u << (slot & 31u);
+        if (!((ld_vol_u32(&shl.req[w]) | ld_vol_u32(&shl.busy[w])) & bit)) atomicOr(&shl.req[w], bit);
+    }
     // neighbours: lane+1 supplies the depth1 lazy maximum, lane+2 the depth2 one (lz.rs:154-169)
-    const uint32_t nb = ((a.w >> 8) & 0xffffu) | fown << 16;
+    const uint32_t room5 = room < 0 ? 0u : (room > 31 ? 31u : (uint32_t)room);
+    const uint32_t nb = ((a.w >> 8) & 0xffffu) | fown << 16 | room5 << 19;
     const uint32_t nb1 = __shfl_down_sync(kFull, nb, 1), nb2 = __shfl_down_sync(kFull, nb, 2);
     const uint32_t key1 = __shfl_down_sync(kFull, key, 1), key2 = __shfl_down_sync(kFull, key, 2);
     const uint32_t lzn1 = nb1 & 0xffu, lzn2 = (nb2 >> 8) & 0xffu;
@@ -645,16 +684,16 @@ __device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t base, 
     const bool is_word = !is_match && x + 1 < sbuf_len && !lazy1 && lwm; // lz.rs:218
     const uint32_t ty = is_match ? kTyMatch : (is_word ? kTyWord : kTyLit);
     const uint32_t adv = is_match ? mlen : (is_word ? 2u : 1u);
-    // what the chase sees: advance (clamped to the block) | type << 8 | true advance << 16; type 3 ends the block at this lane:
-    // code 1 = a record must be repaired first, 2 = a record is not built yet, 3 = next block, 4 = end of the super-window.
-    // The records of x+1 / x+2 only matter if the step evaluates lazy matches; a tight record or a robitlen < 8 that an insert could
-    // flip is exact only for the FIRST step of a super-window.
-    // (the step's own record when tight is checked exactly at verification: `room` further inserts into its bucket keep its oldest
-    // candidate alive; tight records of the lazy neighbours stay first-step-only)
-    const uint32_t m = (fown & 3u) | (lzneed ? ((nb1 | nb2) >> 16) : 0u);
-    const uint32_t room5 = room < 0 ? 0u : (room > 31 ? 31u : (uint32_t)room);
+    // a lane either takes a step or stops the chase: code 1 = a record must be repaired first, 2 = a record is not built yet,
+    // 3 = next block, 4 = end of the super-window.  The records of x+1 / x+2 only matter if the step evaluates lazy matches; a
+    // robitlen < 8 that an insert could flip is exact only for the FIRST step of a super-window.
+    const uint32_t m = (fown & 3u) | (lzneed ? (((nb1 | nb2) >> 16) & 3u) : 0u);
+    // a tight record of a lazy neighbour: exact for a step that has at most `room` steps of the super-window before it (whatever
+    // bucket they insert into) — also checked at verification
+    const uint32_t r1 = (nb1 >> 19) & 31u, r2 = (nb2 >> 19) & 31u;
+    const uint32_t nbroom = lzneed ? (r1 < r2 ? r1 : r2) : 31u;
     const bool first = block0 && lane == 0;
-    const uint32_t scode = (m & 2u) ? 2u : (m & 1u) ? 1u : ((!first && ((m & 4u) || rbsens)) || x >= sbuf_len) ? 4u : lane >= 30 ? 3u : 0u;
+    const uint32_t scode = (m & 2u) ? 2u : (m & 1u) ? 1u : ((!first && rbsens) || x >= sbuf_len) ? 4u : lane >= 30 ? 3u : 0u;
     // (a repair stop also says which of the three records are stale: bit 0 own, 1 x+1, 2 x+2)
     const uint32_t smask = (fown & 1u) | ((nb1 >> 16) & 1u) << 1 | ((nb2 >> 16) & 1u) << 2;
     // The chase of the step chain through this block, from every lane at once (pointer doubling, 5 rounds cover 32 hops): a step lane
@@ -675,7 +714,7 @@ __device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t base, 
     const uint2 pk = make_uint2(msk, nxt | (nxt < 32u ? sinfo << 12 : 0u));
     const uint32_t wu = ty == kTyWord ? 0xffffffffu : (ty == kTyMatch ? wmat : wlit); // lz.rs:208,233
     pk_out[lane] = pk;
-    *reinterpret_cast<uint4 *>(ent_out[lane]) = make_uint4(x, ty | (lzneed ? 4u : 0u) | room5 << 3 | adv << 8 | mlen << 16 | wexp << 24, key1 | (b2 & 0xffu) << 21, key2);
+    *reinterpret_cast<uint4 *>(ent_out[lane]) = make_uint4(x, ty | (lzneed ? 4u : 0u) | room5 << 3 | adv << 8 | mlen << 16 | wexp << 24, key1 | (b2 & 0xffu) << 21, key2 | nbroom << 21);
     *reinterpret_cast<uint4 *>(ent_out[lane] + 4) = make_uint4(key, wu, h2 | lwe << 15, word);
 }
 
@@ -705,6 +744,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
         for (int i = tid; i < kNumBuckets; i += NT) shl.bcnt[i] = shl.lcnt[i] = shl.icnt[i] = S->bcnt[i];
         for (int i = tid; i < 4096; i += NT) shl.lastkey[i] = 0;
         for (int i = tid; i < kRing7; i += NT) shl.sum[i][0] = kNone;
+        for (int i = tid; i < kRing7 / 32; i += NT) shl.req[i] = shl.busy[i] = 0;
         for (int i = tid; i < 32768 / 8; i += NT) reinterpret_cast<uint4 *>(shl.words)[i] = reinterpret_cast<const uint4 *>(S->words)[i];
         if (tid == 0) {
             shl.spos = S->spos;
@@ -750,7 +790,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
             uint32_t n_items = 0, qhead = 0;
             unsigned long long n_windows = 0, n_wait = 0, n_repair = 0, n_rep_rec = 0, n_rep_hard = 0, n_cut = 0, n_handed = 0;
             long long cyc_wait = 0, cyc_walk = 0, cyc_commit = 0, cyc_repair = 0, cyc_load = 0;
-            unsigned long long n_stopc[5] = {0, 0, 0, 0, 0};
+            unsigned long long n_stopc[5] = {0, 0, 0, 0, 0}, n_how[4] = {0, 0, 0, 0}, n_rwait = 0;
             unsigned long long lag_steps = 0, lag_pos = 0, probe_alu = 0, probe_shfl = 0, probe_lds = 0, probe_n = 0;
             const long long t_begin = STATS ? clock64() : 0;
             const unsigned lt_mask = (1u << lane) - 1u;
@@ -864,12 +904,12 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                     }
                     __syncwarp();
                     const uint32_t x = e0.x, ty = e0.y & 3u, lzn = (e0.y >> 2) & 1u, room5 = (e0.y >> 3) & 31u, adv = (e0.y >> 8) & 0xffu, mlen = (e0.y >> 16) & 0xffu, wexp = e0.y >> 24;
-                    const uint32_t key = e1.x, key1 = e0.z & 0x1fffffu, key2 = e0.w, wu = e1.y, h2 = e1.z & 0x7fffu, lwe = e1.z >> 15, word = e1.w;
+                    const uint32_t key = e1.x, key1 = e0.z & 0x1fffffu, key2 = e0.w & 0x1fffffu, nbroom = e0.w >> 21, wu = e1.y, h2 = e1.z & 0x7fffu, lwe = e1.z >> 15, word = e1.w;
                     const uint32_t b2lo = e0.z >> 21;
                     // earlier steps of the super-window that insert into this step's bucket: more than `room` of them and the oldest
                     // candidate of its record has left the ring (matcher.rs:82-87) by the time the step is taken
                     const unsigned mb = __match_any_sync(kFull, live ? key >> 13 : 256u + (uint32_t)lane);
-                    bool viol = (uint32_t)__popc(mb & lt_mask) > room5 + ORZ_V7_MUT_TIGHT;
+                    bool viol = (uint32_t)__popc(mb & lt_mask) > room5 + ORZ_V7_MUT_TIGHT || (uint32_t)lane > nbroom + ORZ_V7_MUT_TIGHT;
                     uint32_t wnext = 32; // the next step of the super-window that writes the same words entry (the last writer wins)
                     // (four steps per trip, their broadcast loads issued together: a lone warp pays the full shared-memory latency otherwise)
                     for (uint32_t j0 = 0; j0 < nst; j0 += 4) {
@@ -960,11 +1000,27 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                         const uint32_t have_y = y;
                         const bool stale = (rmask >> k) & 1u;
                         if (have_y == y && stale && (k == 0 || lzneed0)) {
-                            if (!repair_record7(shl, B, src, y, yslot, spos, qhead, lane)) {
+                            { // the record may be waiting for, or in the middle of, a refresh by its builder: take the request back; a
+                              // refresh that is already running is waited for, then the round is simply taken again
+                                const uint32_t w = yslot >> 5, bit = 1u << (yslot & 31u);
+                                if ((bcast0(ld_vol_u32(&shl.req[w])) | bcast0(ld_vol_u32(&shl.busy[w]))) & bit) {
+                                    if (lane == 0) atomicAnd(&shl.req[w], ~bit);
+                                    __threadfence();
+                                    __syncwarp();
+                                    if (bcast0(ld_vol_u32(&shl.busy[w])) & bit) {
+                                        if (STATS) n_rwait++;
+                                        while (bcast0(ld_vol_u32(&shl.busy[w])) & bit) ORZ_POLL();
+                                        break;
+                                    }
+                                }
+                            }
+                            const int how = repair_record7(shl, B, src, y, yslot, spos, qhead, lane);
+                            if (STATS) n_how[how & 3]++;
+                            if (!how) {
                                 if (STATS) n_rep_hard++;
                                 while (bcast0(ld_vol_u32(v_qdone)) != qhead) ORZ_POLL();
                                 __threadfence();
-                                build_record7(B, y, spos, shl.bcnt, ys, shl.ext[yslot], yslot, lane);
+                                build_record7(B, y, spos, shl.bcnt, ys, shl.ext[yslot], yslot, lane, 2);
                             }
                             if (STATS) n_rep_rec++;
                         }
@@ -1013,6 +1069,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                     S->dbg7[14] += probe_lds;
                     S->dbg7[15] += probe_n;
                     for (int i = 0; i < 5; i++) S->dbg7[16 + i] += n_stopc[i];
+                    for (int i = 1; i < 4; i++) S->dbg7[20 + i] += n_how[i];
+                    S->dbg[6] += n_rwait;
                 }
             }
         } else if (rank == 0 && warp == 1) {
@@ -1233,7 +1291,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 bar_sync7(1, kTeamThreads); // parked until the resolver starts a round (or ends the launch)
                 if (bcast0(ld_vol_u32(v_done))) break;
                 const uint32_t tb = bcast0(ld_vol_u32(&shl.team_base));
-                decide_block7<NBW>(shl, tb + 30u * t, t == 0, sbuf_len, lane, shl.pk_all[t], &shl.ent_all[t * 32u]);
+                decide_block7<NBW>(shl, tb, tb + 30u * t, t == 0, sbuf_len, lane, shl.pk_all[t], &shl.ent_all[t * 32u]);
                 __threadfence_block();
                 __syncwarp();
                 bar_arrive7(2, kTeamThreads);
@@ -1243,30 +1301,68 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
             int bi;
             if (rank == 0) bi = warp - 4 - kTeam7 - (warp - 4 - kTeam7 + 3) / 4;
             else bi = NB0 + ((int)rank - 1) * NW + warp;
-            unsigned long long nbuild = 0;
+            unsigned long long nbuild = 0, nrefresh = 0;
             long long cyc_build = 0;
             const uint32_t last_pos = sbuf_len + 1;
             uint32_t y = S->spos;
             y += ((uint32_t)bi + (uint32_t)NBW - y % (uint32_t)NBW) % (uint32_t)NBW; // first position >= spos owned by this builder
+            const uint32_t first_own = y;
             for (;;) {
-                if (bcast0(ld_vol_u32(v_done))) break;
-                const uint32_t sp = bcast0(ld_vol_u32(v_spos));
-                const uint32_t lp = bcast0(ld_vol_u32(&sh.lead_pos));
+                const uint4 pub = ld_volatile_v4_generic(&sh.spos); // spos, lead_pos, fpos, done
+                if (bcast0(pub.w)) break;
+                const uint32_t sp = bcast0(pub.x), lp = bcast0(pub.y), F = bcast0(pub.z);
                 if (y < sp) y += ((sp - y + (uint32_t)NBW - 1) / (uint32_t)NBW) * (uint32_t)NBW; // the parse went past for good: skip
+                // ---- refresh requests for the records this builder owns that the parse has not reached yet (its newest two positions)
+                bool refreshed = false;
+                uint32_t rw_idx = 0xffffffffu, rw = 0;
+                for (uint32_t j = 1; j <= 2u && j <= (uint32_t)kRing7 / (uint32_t)NBW; j++) {
+                    if (y < first_own + j * (uint32_t)NBW) break;
+                    const uint32_t yy = y - j * (uint32_t)NBW;
+                    if (yy < sp || yy > last_pos) continue;
+                    const uint32_t rslot = slot7<NBW>(yy), w = rslot >> 5, bit = 1u << (rslot & 31u);
+                    if (w != rw_idx) {
+                        rw = bcast0(ld_vol_u32(&sh.req[w]));
+                        rw_idx = w;
+                    }
+                    if (!(rw & bit)) continue;
+                    // take the request: `busy` goes up before `req` comes down, so whoever finds the request gone sees the rebuild running
+                    uint32_t old = 0;
+                    if (lane == 0) {
+                        atomicOr(&sh.busy[w], bit);
+                        __threadfence();
+                        old = atomicAnd(&sh.req[w], ~bit);
+                    }
+                    old = bcast0(old);
+                    if (old & bit) {
+                        if (lane == 0) V7_TRACE("B%d refresh y %u F %u sp %u\n", bi, yy, F, sp);
+                        build_record7(B, yy, F, sh.bcnt, sh.sum[rslot], sh.ext[rslot], rslot, lane, 1);
+                        if (STATS) nrefresh++;
+                        refreshed = true;
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicAnd(&sh.busy[w], ~bit);
+                    rw_idx = 0xffffffffu;
+                }
+                if (refreshed) continue; // (the frontier and the parse position have moved on)
                 // (kLeadMax from `spos` keeps the slot of y - NBW * SL behind everything a fall-back could still need)
                 if (y > last_pos || y > (lp > sp ? lp : sp) + kLead || y > sp + kLeadMax) {
 #ifdef ORZ_SIMT_EMU
                     ORZ_POLL();
 #else
-                    __nanosleep(200);
+                    __nanosleep(400);
 #endif
                     continue;
                 }
-                // The list loads (L2, ld.cg) must be issued after the frontier was read: their address depends on it.
-                const uint32_t F = bcast0(ld_vol_u32(&sh.fpos));
                 if (lane == 0) V7_TRACE("B%d y %u F %u sp %u\n", bi, y, F, sp);
                 const uint32_t yslot = slot7<NBW>(y);
+                { // a request left behind by the slot's previous position must not hit this one
+                    const uint32_t w = yslot >> 5, bit = 1u << (yslot & 31u);
+                    if (w != rw_idx) rw = bcast0(ld_vol_u32(&sh.req[w]));
+                    if ((rw & bit) && lane == 0) atomicAnd(&sh.req[w], ~bit);
+                }
                 const long long tb = STATS ? clock64() : 0;
+                // (the list loads — L2, ld.cg — are issued after the frontier was read: their address depends on it)
                 build_record7(B, y, F, sh.bcnt, sh.sum[yslot], sh.ext[yslot], yslot, lane);
                 if (STATS) {
                     nbuild++;
@@ -1277,6 +1373,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
             if (STATS && lane == 0) {
                 atomicAdd(&S->dbg[4], nbuild);
                 atomicAdd(&S->dbg7[8], (unsigned long long)cyc_build);
+                atomicAdd(&S->dbg[5], nrefresh);
             }
         }
     }
