@@ -921,6 +921,24 @@ void orz_oracle_dec_forward(orz_oracle_dec *d, size_t forward_len) { /* lz.rs:35
     for (int i = 0; i < 256; i++) bucket_forward(&d->ctx.buckets[i], forward_len);
 }
 
+/* test hook: per decoded item (position, value | match length << 16, reduced offset) of the chunks decoded while it is set */
+static uint32_t *g_dec_trace;
+static size_t g_dec_trace_cap, g_dec_trace_n;
+void orz_oracle_dec_set_trace(uint32_t *buf, size_t cap_items) {
+    g_dec_trace = buf;
+    g_dec_trace_cap = cap_items;
+    g_dec_trace_n = 0;
+}
+size_t orz_oracle_dec_trace_len(void) { return g_dec_trace_n; }
+static inline void dec_trace(size_t spos, uint32_t v, size_t match_len, size_t reduced_offset) {
+    if (g_dec_trace && g_dec_trace_n < g_dec_trace_cap) {
+        uint32_t *t = g_dec_trace + 3 * g_dec_trace_n++;
+        t[0] = (uint32_t)spos;
+        t[1] = v | (uint32_t)match_len << 16;
+        t[2] = (uint32_t)reduced_offset;
+    }
+}
+
 /* lz.rs:366-478.  tbuf must be readable for 8 bytes past tlen (decoder refill over-read). */
 int orz_oracle_dec_decode(orz_oracle_dec *self, const uint8_t *tbuf, size_t tlen, uint8_t *sbuf, size_t spos, size_t *spos_end) {
     lzctx_t *ctx = &self->ctx;
@@ -974,12 +992,14 @@ int orz_oracle_dec_decode(orz_oracle_dec *self, const uint8_t *tbuf, size_t tlen
         uint16_t v = symrank_decode(&ctx->symranks[sctx], symbol, lwe0);
 
         if (v == ORZ_WORD_SYMBOL) { /* lz.rs:425-430 */
+            dec_trace(spos, v, 0, 0);
             bucket_update(cur, spos, 0, 0);
             ctx->after_literal = 0;
             sbuf[spos] = lwe0;
             sbuf[spos + 1] = lwe1;
             spos += 2;
         } else if (v < 256) { /* lz.rs:431-437 */
+            dec_trace(spos, v, 0, 0);
             bucket_update(cur, spos, 0, 0);
             ctx->after_literal = 1;
             sbuf[spos] = (uint8_t)v;
@@ -1003,6 +1023,7 @@ int orz_oracle_dec_decode(orz_oracle_dec *self, const uint8_t *tbuf, size_t tlen
             if (eml + match_len_min > match_len_expected) match_len = eml + match_len_min;
             else if (eml > 0) match_len = eml + match_len_min - 1;
             else match_len = match_len_expected;
+            dec_trace(spos, v, match_len, reduced_offset);
             bucket_update(cur, spos, reduced_offset, match_len);
             ctx->after_literal = 0;
             if (match_pos >= spos) return -1; /* corrupt stream: the reference would loop forever / UB */

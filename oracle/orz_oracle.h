@@ -84,6 +84,10 @@ void orz_oracle_dec_forward(orz_oracle_dec *, size_t forward_len);
 /* returns 0, or -1 for InvalidData (lz.rs:413-415) */
 int orz_oracle_dec_decode(orz_oracle_dec *, const uint8_t *tbuf, size_t tlen, uint8_t *sbuf, size_t spos, size_t *spos_end);
 
+/* test hook: while set, every decoded item appends (position, value | match length << 16, reduced offset) to buf (3 words per item) */
+void orz_oracle_dec_set_trace(uint32_t *buf, size_t cap_items);
+size_t orz_oracle_dec_trace_len(void);
+
 /* ---- stream level (src/lib.rs:58-92, 94-129), memory to memory ---- */
 size_t orz_oracle_encode_bound(size_t n);
 /* returns 0 on success, -2 if out_cap is too small */

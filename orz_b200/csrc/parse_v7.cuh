@@ -57,7 +57,7 @@ namespace orz {
 
 constexpr int kListCap = 64;           // entries per key list (circular, newest at (count-1) % 64)
 constexpr int kMaxDepth7 = 48;         // deepest LZCfg depth this kernel handles (levels 0-2 use 45)
-constexpr int kRing7 = 512;            // probe record slots in CTA 0's shared memory
+constexpr int kRing7 = 480;            // probe record slots in CTA 0's shared memory (112 builders x 4, 240 x 2, 6 x 80)
 #ifndef ORZ_V7_LEAD
 #define ORZ_V7_LEAD 96
 #endif
@@ -69,6 +69,12 @@ constexpr int kRing7 = 512;            // probe record slots in CTA 0's shared m
 #endif
 #ifndef ORZ_V7_TEAM
 #define ORZ_V7_TEAM 4
+#endif
+#ifndef ORZ_V7_VERIFY_TABLE
+#define ORZ_V7_VERIFY_TABLE 1 // verification of a super-window with constant work per step (MATCH + a table of lane masks)
+#endif
+#ifndef ORZ_V7_EDGE_EXACT
+#define ORZ_V7_EDGE_EXACT 1 // a robitlen < 8 that an insert could flip ends a round only if the flip would change the decision
 #endif
 constexpr uint32_t kLeadTarget7 = ORZ_V7_LEAD; // how far ahead of the parse records are built: every position of lead is a chance to go stale
 constexpr int kExtCand = 48;           // candidates per record kept for repairs
@@ -179,6 +185,7 @@ struct ParseShared7 {
     uint32_t sidx[32];                      // the super-window's steps: index into ent_all
     uint2 vkw[32];                          // ... and their (key, words update), for the verification loop
     uint32_t lcnt[kNumBuckets], icnt[kNumBuckets]; // the committers' own insert counts (they number the inserts of a batch in order)
+    uint32_t vtab[512];                     // verification: lane masks of the super-window's steps by key hash [0,256) and by words index hash [256,512); all zero between rounds
     // the four words a builder polls, in one 16-byte line: one remote (DSMEM) load per poll instead of four
     uint32_t spos;                          // parse position: every step before it is decided for good (resolver -> builders)
     uint32_t lead_pos;                      // how far the resolver has looked (>= spos; a verification cut may fall back behind it)
@@ -620,6 +627,9 @@ __device__ __forceinline__ int repair_record7(ParseShared7 &shl, const Build7 &B
     return 3;
 }
 
+// table index of a key (21 bits) or a words index (15 bits) for the verification of a super-window
+__device__ __forceinline__ uint32_t vhash7(uint32_t v) { return ((v ^ (v >> 9)) * 0x9E3779B1u) >> 24; }
+
 // Record slots are private to builders: builder b = y % NBW owns SL = 512 / NBW slots and is the only writer of the record of y,
 // (y % NBW) * SL + (y / NBW) % SL.  A builder handles its positions in increasing order, so a build that finishes late (the parse
 // already went past y) can only overwrite that builder's own, older record — never a newer record of another builder.
@@ -675,13 +685,22 @@ __device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t round_
     const uint32_t lwm = lwe == b2 ? 1u : 0u;                       // lz.rs:133
     const uint32_t ro0 = (bc - 1 - word) & kOrdMask;                // reduced offset with no further insert before it (matcher.rs:185)
     const uint32_t rb = ro0 < 510u ? 1u : 0u;                       // robitlen < 8  <=>  reduced offset < 510
-    const bool rbsens = mlen > 0 && ro0 < 510u && ro0 + 31u >= 510u; // an insert of this super-window could flip robitlen < 8
     // lz.rs:146-236, spelled out without branches
     const uint32_t l1 = mlen + 1 + rb, l2 = l1 - lwm;               // lz.rs:152-153
     const bool lazy1 = lzneed && lzn1 >= l1;
     const bool lazy2 = lzneed && !lazy1 && lzn2 >= l2;
     const bool is_match = mlen > 0 && !lazy1 && !lazy2;
     const bool is_word = !is_match && x + 1 < sbuf_len && !lazy1 && lwm; // lz.rs:218
+    // An insert of this super-window into the bucket could flip robitlen < 8 (the reduced offset only grows: 1 -> 0).  The
+    // flag only enters the two lazy thresholds (lz.rs:152-153; the emitted code comes from the committer's own ordinals), so
+    // the step is sensitive only if the decision taken with the other value differs.
+#if ORZ_V7_EDGE_EXACT
+    const bool lazy1f = lzneed && lzn1 >= mlen + 1;
+    const bool lazy2f = lzneed && !lazy1f && lzn2 >= mlen + 1 - lwm;
+    const bool rbsens = lzneed && ro0 < 510u && ro0 + 31u >= 510u && (lazy1f != lazy1 || lazy2f != lazy2);
+#else
+    const bool rbsens = mlen > 0 && ro0 < 510u && ro0 + 31u >= 510u;
+#endif
     const uint32_t ty = is_match ? kTyMatch : (is_word ? kTyWord : kTyLit);
     const uint32_t adv = is_match ? mlen : (is_word ? 2u : 1u);
     // a lane either takes a step or stops the chase: code 1 = a record must be repaired first, 2 = a record is not built yet,
@@ -743,6 +762,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
         for (int i = tid; i < kNumCtx; i += NT) shl.cnt[i] = 0;
         for (int i = tid; i < kNumBuckets; i += NT) shl.bcnt[i] = shl.lcnt[i] = shl.icnt[i] = S->bcnt[i];
         for (int i = tid; i < 4096; i += NT) shl.lastkey[i] = 0;
+        for (int i = tid; i < 512; i += NT) shl.vtab[i] = 0;
         for (int i = tid; i < kRing7; i += NT) shl.sum[i][0] = kNone;
         for (int i = tid; i < kRing7 / 32; i += NT) shl.req[i] = shl.busy[i] = 0;
         for (int i = tid; i < 32768 / 8; i += NT) reinterpret_cast<uint4 *>(shl.words)[i] = reinterpret_cast<const uint4 *>(S->words)[i];
@@ -900,7 +920,9 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                         const uint32_t *ent = shl.ent_all[shl.sidx[lane]];
                         e0 = *reinterpret_cast<const uint4 *>(ent);
                         e1 = *reinterpret_cast<const uint4 *>(ent + 4);
+#if !ORZ_V7_VERIFY_TABLE
                         shl.vkw[lane] = make_uint2(e1.x, e1.y);
+#endif
                     }
                     __syncwarp();
                     const uint32_t x = e0.x, ty = e0.y & 3u, lzn = (e0.y >> 2) & 1u, room5 = (e0.y >> 3) & 31u, adv = (e0.y >> 8) & 0xffu, mlen = (e0.y >> 16) & 0xffu, wexp = e0.y >> 24;
@@ -910,6 +932,49 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                     // candidate of its record has left the ring (matcher.rs:82-87) by the time the step is taken
                     const unsigned mb = __match_any_sync(kFull, live ? key >> 13 : 256u + (uint32_t)lane);
                     bool viol = (uint32_t)__popc(mb & lt_mask) > room5 + ORZ_V7_MUT_TIGHT || (uint32_t)lane > nbroom + ORZ_V7_MUT_TIGHT;
+#if ORZ_V7_VERIFY_TABLE
+                    // Constant work per step instead of one pass per earlier step.  Same key as an earlier step, and the later
+                    // writers of this step's words entry: one MATCH each.  The cross questions — did an earlier step insert a node
+                    // with the key of x+1 / x+2 (lazy neighbours), did one write the words entry this step read — go through a small
+                    // table of lane masks (entry = the steps whose key / words index hashes there; every candidate is confirmed).
+                    const bool writer = live && wu != 0xffffffffu;
+                    const uint32_t widx = wu & 0x7fffu;
+                    const unsigned mk = __match_any_sync(kFull, live ? key : 0x40000000u | (uint32_t)lane);
+                    const unsigned mw = __match_any_sync(kFull, writer ? widx : 0x40000000u | (uint32_t)lane);
+                    viol = viol || (mk & lt_mask) != 0u;
+                    const unsigned wlater = mw & ~lt_mask & ~(1u << lane); // later steps that write the same words entry (the last writer wins)
+                    if (live) atomicOr(&shl.vtab[vhash7(key)], 1u << lane);
+                    if (writer) atomicOr(&shl.vtab[256u + vhash7(widx)], 1u << lane);
+                    __syncwarp();
+                    unsigned m1 = 0, m2 = 0, m3 = 0;
+                    if (live) {
+                        if (lzn) {
+                            m1 = shl.vtab[vhash7(key1)] & lt_mask;
+                            m2 = shl.vtab[vhash7(key2)] & lt_mask;
+                        }
+                        m3 = shl.vtab[256u + vhash7(h2)] & lt_mask;
+                    }
+                    __syncwarp();
+                    if (live) shl.vtab[vhash7(key)] = 0u;
+                    if (writer) shl.vtab[256u + vhash7(widx)] = 0u;
+                    while (__ballot_sync(kFull, (m1 | m2) != 0u)) { // earlier steps whose key shares a table entry with x+1's / x+2's
+                        const int b1 = m1 ? 31 - __clz(m1) : 0, b2 = m2 ? 31 - __clz(m2) : 0;
+                        const uint32_t k1 = __shfl_sync(kFull, key, b1), k2 = __shfl_sync(kFull, key, b2);
+                        viol = viol || (m1 && k1 == key1) || (m2 && k2 == key2);
+                        if (m1) m1 &= ~(1u << b1);
+                        if (m2) m2 &= ~(1u << b2);
+                    }
+                    while (__ballot_sync(kFull, m3 != 0u)) { // the latest earlier writer of the words entry this step read decides (lz.rs:132,208,233)
+                        const int b3 = m3 ? 31 - __clz(m3) : 0;
+                        const uint32_t w3 = __shfl_sync(kFull, wu, b3);
+                        if (m3) {
+                            if ((w3 & 0x7fffu) == h2) {
+                                viol = viol || (w3 >> 15) != lwe;
+                                m3 = 0u;
+                            } else m3 &= ~(1u << b3);
+                        }
+                    }
+#else
                     uint32_t wnext = 32; // the next step of the super-window that writes the same words entry (the last writer wins)
                     // (four steps per trip, their broadcast loads issued together: a lone warp pays the full shared-memory latency otherwise)
                     for (uint32_t j0 = 0; j0 < nst; j0 += 4) {
@@ -927,6 +992,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                             if (j > (uint32_t)lane && j < nst && wnext == 32u && wj != 0xffffffffu && wu != 0xffffffffu && wi == (wu & 0x7fffu)) wnext = j;
                         }
                     }
+                    const unsigned wlater = wnext < 32u ? 1u << wnext : 0u;
+#endif
                     const unsigned vm = __ballot_sync(kFull, viol && live);
                     uint32_t nok = nst;
                     if (vm) {
@@ -956,7 +1023,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                         shl.queue[(qhead + (uint32_t)lane) % kQueue7] = rec;
                         atomicAdd(&shl.bcnt[key >> 13], 1u);
                         atomicMax(&shl.lastkey[(key ^ (key >> 9)) & 4095u], x);
-                        if (ty != kTyWord && wnext >= nok) shl.words[wu & 0x7fffu] = (uint16_t)(wu >> 15);
+                        if (ty != kTyWord && !(wlater & ((nok < 32u ? 1u << nok : 0u) - 1u))) shl.words[wu & 0x7fffu] = (uint16_t)(wu >> 15);
                     }
                     after_literal = __shfl_sync(kFull, ty, (int)nok - 1) == kTyLit ? 1u : 0u;
                     (void)adv;

@@ -38,6 +38,11 @@ def main():
         res = {"bytes": n, "level": level, "wall_s": round(wall, 4), "mb_s": round(n / wall / 1e6, 3), "identical": got == want,
                "oracle_mb_s": round(n / t_cpu / 1e6, 2), "out_len": len(got), "want_len": len(want),
                "ms": {name: [round(x, 2) for x in b.timing(c)] for c, name in enumerate(["parse", "emit", "block", "decode", "run"])}}
+        if got != want:
+            m = min(len(got), len(want))
+            fd = next((i for i in range(0, m, 4096) if got[i:i + 4096] != want[i:i + 4096]), m)
+            fd = next((i for i in range(fd, min(fd + 4096, m)) if got[i] != want[i]), fd)
+            res["first_diff"] = fd
         b.close()
     print(json.dumps(res), flush=True)
 
