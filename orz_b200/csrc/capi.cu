@@ -139,6 +139,7 @@ struct orz_batch {
     bool v7 = false;         // encoder state in the v7 layout (key lists), else ring records + hash chains
     KernelTimer timer;
     bool ran = false;
+    void *prov = nullptr;    // ORZ_B200_PROV: per-step provenance of stream 0 (A/B builds, see EncStream::prov)
 };
 
 static int check_device(int device) {
@@ -200,6 +201,7 @@ static void batch_destroy(orz_batch *b) {
     DevGuard g(b->device);
     if (b->st) cudaStreamSynchronize(b->st);
     if (b->arena) cudaFree(b->arena);
+    if (b->prov) cudaFree(b->prov);
     if (b->h_status_pinned) cudaFreeHost(b->h_status_pinned);
     if (b->st2) {
         cudaStreamSynchronize(b->st2);
@@ -369,6 +371,23 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
             S.depth2 = (uint32_t)(cfg->lazy_match_depth2 > 0x7fffffffu ? 0x7fffffffu : cfg->lazy_match_depth2);
             S.self_driven = chunk_mode ? 0 : 1;
             S.dbg_flags = getenv("ORZ_B200_DBG") ? (uint32_t)atoi(getenv("ORZ_B200_DBG")) : 0u;
+            S.dbg_pos = getenv("ORZ_B200_DBG_POS") ? (uint32_t)strtoul(getenv("ORZ_B200_DBG_POS"), nullptr, 10) : 0u;
+            S.dbg_inpos = getenv("ORZ_B200_DBG_INPOS") ? strtoull(getenv("ORZ_B200_DBG_INPOS"), nullptr, 10) : 0ull;
+            S.dbgx_n = 0;
+            S.prov = nullptr;
+            S.prov_cap = S.prov_n = 0;
+#ifndef ORZ_SIMT_EMU
+            if (i == 0 && v7 && getenv("ORZ_B200_PROV")) { // debugging aid of the A/B builds: provenance of every parse step (stream 0 only)
+                const size_t cap = in_len[i] / 3 + (2u << 20);
+                void *p = nullptr;
+                if (cudaMalloc(&p, cap * 32) == cudaSuccess) {
+                    cudaMemset(p, 0, cap * 32);
+                    S.prov = reinterpret_cast<uint4 *>(p);
+                    S.prov_cap = (uint32_t)cap;
+                    b->prov = p;
+                }
+            }
+#endif
             S.first_block = 1;   // lz.rs:63
             S.after_literal = 1; // lz.rs:64
             b->d_in[i] = A + o.in;
@@ -514,7 +533,20 @@ extern "C" int orz_batch_run(orz_batch *b) {
                     d[0], d[1], (double)d[0] / wn, d[2], d[3], d[3] / st, c[6], c[21], c[22], c[23], c[7], d[4], d[4] / st, d[4] ? (double)c[8] / d[4] : 0.0, d[5], d[6], c[9] / wn, c[10] / wn,
                     c[0] / st, c[1] / st, c[2] / st, c[3] / st, c[4] / st, c[5] / st, c[11], c[16] + c[19], c[17], c[18], c[20], c[15] ? (double)c[12] / c[15] : 0.0,
                     c[15] ? (double)c[13] / c[15] : 0.0, c[15] ? (double)c[14] / c[15] : 0.0);
-        } else if (getenv("ORZ_B200_STATS")) {
+        }
+        if (b->v7 && getenv("ORZ_B200_DBG_POS")) {
+            for (int i = 0; i < b->n; i++) { // the event trace of ORZ_B200_DBG_POS: tag | words << 24, then the words
+                const uint32_t nx = tmp[i].dbgx_n < 1024u ? tmp[i].dbgx_n : 1024u;
+                for (uint32_t k = 0; k < nx;) {
+                    const uint32_t tag = tmp[i].dbgx[k] & 0xffffffu, nw = tmp[i].dbgx[k] >> 24;
+                    fprintf(stderr, "orz_b200 trace: %s", tag == 1 ? "build" : tag == 2 ? "repair" : tag == 3 ? "hand-over" : tag == 4 ? "decide" : tag == 5 ? "candidates" : "?");
+                    for (uint32_t w = 1; w <= nw && k + w < 1024u; w++) fprintf(stderr, " %u", tmp[i].dbgx[k + w]);
+                    fprintf(stderr, "\n");
+                    k += nw + 1;
+                }
+            }
+        }
+        if (!(b->v7 && parse7_stats_enabled()) && getenv("ORZ_B200_STATS")) {
             unsigned long long d[8] = {0};
             for (int i = 0; i < b->n; i++)
                 for (int k = 0; k < 8; k++) d[k] += tmp[i].dbg[k];
@@ -570,6 +602,13 @@ extern "C" int orz_batch_download(orz_batch *b, int i, uint8_t *host, size_t cap
 extern "C" void *orz_batch_result_dev(orz_batch *b, int i) {
     if (!b || i < 0 || i >= b->n) return nullptr;
     return b->d_out[i];
+}
+
+// debugging aid (not part of include/orz_b200.h): the two uint4 of provenance that stage A left for item `index` of stream 0
+extern "C" int orz_b200_debug_prov(orz_batch *b, size_t index, uint32_t *out8) {
+    if (!b || !b->prov || !out8) return ORZ_EARG;
+    DevGuard g(b->device);
+    return cudaMemcpy(out8, reinterpret_cast<const uint8_t *>(b->prov) + index * 32, 32, cudaMemcpyDeviceToHost) == cudaSuccess ? ORZ_OK : ORZ_ECUDA;
 }
 
 extern "C" int orz_batch_timing(orz_batch *b, int cls, float *total_ms, int *launches) {

@@ -169,6 +169,15 @@ struct EncStream {
     uint32_t ctx_count_alt[kNumCtx];
     unsigned long long dbg[8]; // stage A counters: steps, executor spin iterations (own / lazy1 / lazy2 probe), builds, aborted builds
     unsigned long long dbg7[24]; // v7: resolver cycles total, load, walk, hand-over, repair, wait; records repaired, rebuilt from HBM; builder cycles; list lag
+    // event trace of one position (instrumented build only; ORZ_B200_DBG_POS = window position, ORZ_B200_DBG_INPOS = input bytes
+    // consumed when its block is loaded): builds, repairs, decisions and the hand-over of the records at that position and the two after it
+    unsigned long long dbg_inpos;
+    uint32_t dbg_pos;
+    uint32_t dbgx_n;
+    uint32_t dbgx[1024];
+    // per-step provenance of the parse (A/B builds with ORZ_V7_PROV, ORZ_B200_PROV=1): two uint4 per item of the whole stream
+    uint4 *prov;
+    uint32_t prov_cap, prov_n;
 };
 
 // Per-stream decoder control block (lz.rs:348-357 LZDecoder, lib.rs:99-127 loop state)

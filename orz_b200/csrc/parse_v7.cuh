@@ -73,6 +73,12 @@ constexpr int kRing7 = 480;            // probe record slots in CTA 0's shared m
 #ifndef ORZ_V7_VERIFY_TABLE
 #define ORZ_V7_VERIFY_TABLE 1 // verification of a super-window with constant work per step (MATCH + a table of lane masks)
 #endif
+#ifndef ORZ_V7_TRACE_ALWAYS
+#define ORZ_V7_TRACE_ALWAYS 0 // 1: the event trace of ORZ_B200_DBG_POS is compiled into the production instantiation too (A/B builds only)
+#endif
+#ifndef ORZ_V7_PROV
+#define ORZ_V7_PROV 0 // 1: every handed-over step leaves two uint4 of provenance (how its record came about) in EncStream::prov (A/B builds only)
+#endif
 #ifndef ORZ_V7_EDGE_EXACT
 #define ORZ_V7_EDGE_EXACT 1 // a robitlen < 8 that an insert could flip ends a round only if the flip would change the decision
 #endif
@@ -260,7 +266,18 @@ __device__ __forceinline__ void fm_round(FmState &st, bool valid, int lcp, uint3
     }
 }
 
+// event trace of one position (instrumented build only): see EncStream::dbgx
+__device__ __forceinline__ void trace7(EncStream *S, uint32_t tag, const uint32_t *v, int n) {
+    const uint32_t i = atomicAdd(&S->dbgx_n, (uint32_t)(n + 1));
+    if (i + (uint32_t)n + 1u <= 1024u) {
+        S->dbgx[i] = tag | (uint32_t)n << 24;
+        for (int k = 0; k < n; k++) S->dbgx[i + 1 + k] = v[k];
+    }
+}
+
 struct Build7 {
+    EncStream *S;
+    uint32_t dbg_pos;     // 0, or the window position whose records are traced (instrumented build)
     const uint8_t *win;
     const uint2 *klist;
     const uint32_t *kcnt;
@@ -388,6 +405,15 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
         wv_m = t2 & 0xffffu;
     }
     ORZ_COST(200);
+    if (B.dbg_pos && y - B.dbg_pos < 3u) { // (instrumented builds) the first four candidates: position, lcp | expected << 8
+        uint32_t tv[9];
+        tv[0] = y;
+        for (int i = 0; i < 4; i++) {
+            tv[1 + 2 * i] = __shfl_sync(kFull, ok0 ? p0 : 0u, i);
+            tv[2 + 2 * i] = __shfl_sync(kFull, ok0 ? ((uint32_t)lcp0 | kentry_exp(en) << 8) : 0xffffffffu, i);
+        }
+        if (lane == 0) trace7(B.S, 5u, tv, 9);
+    }
     // ---- publish: ext (all lanes), summary words 1.. (lane 0), fence, stamp
     uint32_t stampv = y;
     if (mode) {
@@ -419,6 +445,15 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
         sum[7] = hw_lit | wv_lit << 15;
         sum[8] = hw_m | wv_m << 15;
         sum[9] = (uint32_t)(mf < 0 ? 0 : mf) | (uint32_t)(m1m < 0 ? 0 : m1m) << 8 | (uint32_t)(m2m < 0 ? 0 : m2m) << 16;
+#if ORZ_V7_PROV
+        sum[10] = (cnt & 0xffffu) | (r & 15u) << 16 | ((uint32_t)n0 & 63u) << 20 | ((uint32_t)mode & 3u) << 26; // bits 28-29: last repair, 30-31: repairs
+        sum[11] = gc;
+#endif
+        if (B.dbg_pos && y - B.dbg_pos < 3u) {
+            const uint32_t tv[14] = {y, F, cnt, r, (uint32_t)n0 | (uint32_t)n1 << 8 | (uint32_t)ncand << 16 | (incomplete ? 1u : 0u) << 24, gc, mlen | c1 << 8 | c2 << 16 | wexp << 24,
+                                     (uint32_t)mode, word, (uint32_t)st.best, st.exp_best, ord0, ordmin, avail};
+            trace7(B.S, 1u, tv, 14);
+        }
     }
     // the barrier orders every lane's stores before lane 0's release store of the stamp (cumulative: no fence per lane)
     __syncwarp();
@@ -644,7 +679,7 @@ __device__ __forceinline__ uint32_t slot7(uint32_t y) {
 // the first step of the super-window (records that are exact only for a first step are usable there).
 template <int NBW>
 __device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t round_base, uint32_t base, bool block0, uint32_t sbuf_len, int lane, uint2 *pk_out,
-                                              uint32_t (*ent_out)[8]) {
+                                              uint32_t (*ent_out)[8], EncStream *S, uint32_t dbg_pos) {
     const uint32_t x = base + (uint32_t)lane;
     const uint32_t *rs = shl.sum[slot7<NBW>(x)];
     // The stamp is the builder's last store (release); the first 16 bytes are read in one shared-memory transaction, the rest
@@ -732,6 +767,10 @@ __device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t round_
     // x = lanes stepped on; y = end (lane or position relative to the block) | stop code << 12 | stale mask << 16
     const uint2 pk = make_uint2(msk, nxt | (nxt < 32u ? sinfo << 12 : 0u));
     const uint32_t wu = ty == kTyWord ? 0xffffffffu : (ty == kTyMatch ? wmat : wlit); // lz.rs:208,233
+    if (dbg_pos && x - dbg_pos < 3u) {
+        const uint32_t tv[10] = {x, round_base, fown | scode << 4 | ty << 8 | (lzneed ? 1u : 0u) << 12, lk, F, mlen | lzn1 << 8 | lzn2 << 16, lwm | rb << 1, ro0, a.x, bc};
+        trace7(S, 4u, tv, 10);
+    }
     pk_out[lane] = pk;
     *reinterpret_cast<uint4 *>(ent_out[lane]) = make_uint4(x, ty | (lzneed ? 4u : 0u) | room5 << 3 | adv << 8 | mlen << 16 | wexp << 24, key1 | (b2 & 0xffu) << 21, key2 | nbroom << 21);
     *reinterpret_cast<uint4 *>(ent_out[lane] + 4) = make_uint4(key, wu, h2 | lwe << 15, word);
@@ -788,6 +827,8 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
     if (active) {
         const uint32_t sbuf_len = S->sbuf_len;
         Build7 B;
+        B.S = S;
+        B.dbg_pos = ((STATS || ORZ_V7_TRACE_ALWAYS) && S->dbg_pos != 0u && S->in_pos == S->dbg_inpos) ? S->dbg_pos : 0u;
         B.win = S->win;
         B.klist = S->klist;
         B.kcnt = S->kcnt;
@@ -1021,6 +1062,21 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                         rec.z = key | (ty == kTyMatch ? mlen : 0u) << 21;
                         rec.w = wexp | (lwe & 0xffu) << 8 | b2lo << 16;
                         shl.queue[(qhead + (uint32_t)lane) % kQueue7] = rec;
+#if ORZ_V7_PROV
+                        if (S->prov) {
+                            const uint32_t pi = S->prov_n + n_items + (uint32_t)lane;
+                            const uint32_t pslot = slot7<NBW>(x);
+                            const uint32_t *prs = shl.sum[pslot];
+                            if (pi < S->prov_cap) {
+                                S->prov[2 * (size_t)pi] = make_uint4(x, prs[1], prs[3], prs[10]);
+                                S->prov[2 * (size_t)pi + 1] = make_uint4(prs[6], prs[11], shl.ext[pslot][1], ty | mlen << 8 | (uint32_t)lane << 16 | nst << 24);
+                            }
+                        }
+#endif
+                        if ((STATS || ORZ_V7_TRACE_ALWAYS) && B.dbg_pos && x - B.dbg_pos < 3u) {
+                            const uint32_t tv[9] = {x, ty, mlen, word, (uint32_t)lane, nst, nok, key, wexp};
+                            trace7(S, 3u, tv, 9);
+                        }
                         atomicAdd(&shl.bcnt[key >> 13], 1u);
                         atomicMax(&shl.lastkey[(key ^ (key >> 9)) & 4095u], x);
                         if (ty != kTyWord && !(wlater & ((nok < 32u ? 1u << nok : 0u) - 1u))) shl.words[wu & 0x7fffu] = (uint16_t)(wu >> 15);
@@ -1083,6 +1139,17 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                             }
                             const int how = repair_record7(shl, B, src, y, yslot, spos, qhead, lane);
                             if (STATS) n_how[how & 3]++;
+#if ORZ_V7_PROV
+                            if (lane == 0) {
+                                const uint32_t w = ys[10];
+                                ys[10] = (w & 0x0fffffffu) | ((uint32_t)how & 3u) << 28 | ((((w >> 30) + 1u) > 3u ? 3u : (w >> 30) + 1u)) << 30;
+                            }
+                            __syncwarp();
+#endif
+                            if ((STATS || ORZ_V7_TRACE_ALWAYS) && B.dbg_pos && y - B.dbg_pos < 3u && lane == 0) {
+                                const uint32_t tv[13] = {y, spos, (uint32_t)how, ys[3], ys[4], ys[5], ys[6], shl.rc_pos[0], shl.rc_exp[0], shl.rc_ord[0], shl.ext[yslot][0], shl.ext[yslot][1], ys[1]};
+                                trace7(S, 2u, tv, 13);
+                            }
                             if (!how) {
                                 if (STATS) n_rep_hard++;
                                 while (bcast0(ld_vol_u32(v_qdone)) != qhead) ORZ_POLL();
@@ -1115,6 +1182,9 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 S->spos = spos;
                 S->after_literal = after_literal;
                 (buf ? S->n_items_alt : S->n_items) = n_items;
+#if ORZ_V7_PROV
+                S->prov_n += n_items;
+#endif
                 if (STATS) {
                     S->dbg[0] += n_items;
                     S->dbg[1] += n_windows;
@@ -1358,7 +1428,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 bar_sync7(1, kTeamThreads); // parked until the resolver starts a round (or ends the launch)
                 if (bcast0(ld_vol_u32(v_done))) break;
                 const uint32_t tb = bcast0(ld_vol_u32(&shl.team_base));
-                decide_block7<NBW>(shl, tb, tb + 30u * t, t == 0, sbuf_len, lane, shl.pk_all[t], &shl.ent_all[t * 32u]);
+                decide_block7<NBW>(shl, tb, tb + 30u * t, t == 0, sbuf_len, lane, shl.pk_all[t], &shl.ent_all[t * 32u], S, (STATS || ORZ_V7_TRACE_ALWAYS) ? B.dbg_pos : 0u);
                 __threadfence_block();
                 __syncwarp();
                 bar_arrive7(2, kTeamThreads);

@@ -67,31 +67,42 @@ class Dec:
         return payload, rows
 
 
-def main():
-    got = open(sys.argv[1], "rb").read()
-    want = open(sys.argv[2], "rb").read()
-    ctx = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+def first_difference(got, want):
+    """-> None, or (chunk index, item index in the chunk, items before the chunk, rows of got, rows of want)"""
     a, b = Dec(got), Dec(want)
-    ci = 0
+    ci = before = 0
     while True:
         ca, cb = a.next_chunk(), b.next_chunk()
         if ca is None or cb is None:
-            print("streams end" + ("" if ca is None and cb is None else " at different chunks"))
-            return
+            return None
         if ca[0] != cb[0]:
             ra, rb = ca[1], cb[1]
             m = min(len(ra), len(rb))
             neq = np.nonzero((ra[:m] != rb[:m]).any(axis=1))[0]
-            k = int(neq[0]) if len(neq) else m
-            print(f"chunk {ci}: {len(ra)} vs {len(rb)} items, first differing item {k}")
-            for name, r in (("got", ra), ("want", rb)):
-                print(f"  {name}:")
-                for i in range(max(0, k - ctx), min(len(r), k + ctx)):
-                    pos, v, ml, ro = (int(x) for x in r[i])
-                    what = f"literal {v}" if v < 256 else (f"match len {ml} ro {ro} (sym {v})" if ml else f"WORD (sym {v})")
-                    print(f"   {'>' if i == k else ' '} item {i} pos {pos}: {what}")
-            return
+            return ci, (int(neq[0]) if len(neq) else m), before, ra, rb
+        before += len(ca[1])
         ci += 1
+
+
+def show(diff, ctx=6, out=sys.stdout):
+    ci, k, before, ra, rb = diff
+    print(f"chunk {ci}: {len(ra)} vs {len(rb)} items, first differing item {k} (item {before + k} of the stream)", file=out)
+    for name, r in (("got", ra), ("want", rb)):
+        print(f"  {name}:", file=out)
+        for i in range(max(0, k - ctx), min(len(r), k + ctx)):
+            pos, v, ml, ro = (int(x) for x in r[i])
+            what = f"literal {v}" if v < 256 else (f"match len {ml} ro {ro} (sym {v})" if ml else f"WORD (sym {v})")
+            print(f"   {'>' if i == k else ' '} item {i} pos {pos}: {what}", file=out)
+
+
+def main():
+    got = open(sys.argv[1], "rb").read()
+    want = open(sys.argv[2], "rb").read()
+    d = first_difference(got, want)
+    if d is None:
+        print("no chunk differs")
+    else:
+        show(d, int(sys.argv[3]) if len(sys.argv) > 3 else 6)
 
 
 if __name__ == "__main__":
