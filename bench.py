@@ -362,13 +362,20 @@ def main():
         kernel = "orz_parse7_kernel<16,%s>" % os.environ.get("ORZ_B200_V7_CLUSTER", "8")
     else:
         kernel = "orz_parse4_kernel<16,4>" if n == 1 else ("orz_parse_kernel<22,16>" if n <= 296 else "orz_parse_kernel<11,8>")
-    traffic = None
+    # DRAM traffic of the kernel from the committed ncu --set full capture (profiles/traffic.json), scaled from the captured launch to
+    # this run's average launch by the algorithmic bytes of the two (the capture is of a shorter launch of the same kernel)
+    traffic = traffic_src = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(kernel.split("<")[0] + "_dram_bytes_per_launch")  # from one ncu --set full capture
+            tj = json.load(open(tp))
+            key = kernel.split("<")[0]
+            if key + "_dram_bytes_per_launch" in tj:
+                cap_alg = float(tj.get(key + "_algorithmic_bytes_that_launch", 0) or 0)
+                traffic = float(tj[key + "_dram_bytes_per_launch"]) * ((alg_bytes / p_launch) / cap_alg if cap_alg > 0 else 1.0)
+                traffic_src = tj.get(key + "_source")
         except Exception:
-            traffic = None
+            traffic = traffic_src = None
     out = dict(base)
     out["config"] = dict(config, stage_a=kernel, bit_identical_to_oracle=identical,
                          oracle_pin="two independent restatements agree; NOT pinned against real orz bytes (no Rust toolchain; tools/make_ref_golden.sh)")
@@ -382,7 +389,7 @@ def main():
         "gpu_launches": int(sum(launches)),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes / p_launch, "launches_per_step": p_launch,
                      "avg_launch_ms": p_ms / p_launch,
                      "note": "one orz stream is ONE serial dependency chain (SURVEY 0-2): the kernel is bound by dependent-instruction and "

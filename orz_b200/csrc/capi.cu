@@ -378,10 +378,10 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
             S.prov_cap = S.prov_n = 0;
 #ifndef ORZ_SIMT_EMU
             if (i == 0 && v7 && getenv("ORZ_B200_PROV")) { // debugging aid of the A/B builds: provenance of every parse step (stream 0 only)
-                const size_t cap = in_len[i] / 3 + (2u << 20);
+                const size_t cap = in_len[i] + 1024;
                 void *p = nullptr;
-                if (cudaMalloc(&p, cap * 32) == cudaSuccess) {
-                    cudaMemset(p, 0, cap * 32);
+                if (cudaMalloc(&p, cap * 48) == cudaSuccess) {
+                    cudaMemset(p, 0, cap * 48);
                     S.prov = reinterpret_cast<uint4 *>(p);
                     S.prov_cap = (uint32_t)cap;
                     b->prov = p;
@@ -604,11 +604,11 @@ extern "C" void *orz_batch_result_dev(orz_batch *b, int i) {
     return b->d_out[i];
 }
 
-// debugging aid (not part of include/orz_b200.h): the two uint4 of provenance that stage A left for item `index` of stream 0
-extern "C" int orz_b200_debug_prov(orz_batch *b, size_t index, uint32_t *out8) {
-    if (!b || !b->prov || !out8) return ORZ_EARG;
+// debugging aid (not part of include/orz_b200.h): the three uint4 of provenance that stage A left for input position `index` of stream 0
+extern "C" int orz_b200_debug_prov(orz_batch *b, size_t index, uint32_t *out12) {
+    if (!b || !b->prov || !out12) return ORZ_EARG;
     DevGuard g(b->device);
-    return cudaMemcpy(out8, reinterpret_cast<const uint8_t *>(b->prov) + index * 32, 32, cudaMemcpyDeviceToHost) == cudaSuccess ? ORZ_OK : ORZ_ECUDA;
+    return cudaMemcpy(out12, reinterpret_cast<const uint8_t *>(b->prov) + index * 48, 48, cudaMemcpyDeviceToHost) == cudaSuccess ? ORZ_OK : ORZ_ECUDA;
 }
 
 extern "C" int orz_batch_timing(orz_batch *b, int cls, float *total_ms, int *launches) {

@@ -175,7 +175,7 @@ struct EncStream {
     uint32_t dbg_pos;
     uint32_t dbgx_n;
     uint32_t dbgx[1024];
-    // per-step provenance of the parse (A/B builds with ORZ_V7_PROV, ORZ_B200_PROV=1): two uint4 per item of the whole stream
+    // provenance of the probe records (A/B builds with ORZ_V7_PROV, ORZ_B200_PROV=1): three uint4 per input position (build, build, last repair)
     uint4 *prov;
     uint32_t prov_cap, prov_n;
 };

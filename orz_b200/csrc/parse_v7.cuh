@@ -160,6 +160,11 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.cluster.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 #endif
 }
+__device__ __forceinline__ void fence_cluster7() {
+#ifndef ORZ_SIMT_EMU
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ uint32_t ldcg_u32(const uint32_t *p) {
 #ifdef ORZ_SIMT_EMU
     return *p;
@@ -278,6 +283,7 @@ __device__ __forceinline__ void trace7(EncStream *S, uint32_t tag, const uint32_
 struct Build7 {
     EncStream *S;
     uint32_t dbg_pos;     // 0, or the window position whose records are traced (instrumented build)
+    uint32_t prov_base;   // absolute input offset of window position PREMATCH (provenance log of the A/B builds)
     const uint8_t *win;
     const uint2 *klist;
     const uint32_t *kcnt;
@@ -446,8 +452,13 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
         sum[8] = hw_m | wv_m << 15;
         sum[9] = (uint32_t)(mf < 0 ? 0 : mf) | (uint32_t)(m1m < 0 ? 0 : m1m) << 8 | (uint32_t)(m2m < 0 ? 0 : m2m) << 16;
 #if ORZ_V7_PROV
-        sum[10] = (cnt & 0xffffu) | (r & 15u) << 16 | ((uint32_t)n0 & 63u) << 20 | ((uint32_t)mode & 3u) << 26; // bits 28-29: last repair, 30-31: repairs
-        sum[11] = gc;
+        if (B.S->prov) { // provenance of the build, by absolute input position (three uint4 per position: build, build, last repair)
+            const size_t pi = (size_t)B.prov_base + (y - kPrematch);
+            if (y >= kPrematch && pi < (size_t)B.S->prov_cap) {
+                B.S->prov[3 * pi] = make_uint4(F, cnt, r | (uint32_t)mode << 8 | (uint32_t)n0 << 16 | (uint32_t)n1 << 24, gc);
+                B.S->prov[3 * pi + 1] = make_uint4((uint32_t)ncand | (incomplete ? 1u : 0u) << 8 | ((uint32_t)st.best & 0xffu) << 16, mlen | c1 << 8 | c2 << 16 | wexp << 24, en.x, en.y);
+            }
+        }
 #endif
         if (B.dbg_pos && y - B.dbg_pos < 3u) {
             const uint32_t tv[14] = {y, F, cnt, r, (uint32_t)n0 | (uint32_t)n1 << 8 | (uint32_t)ncand << 16 | (incomplete ? 1u : 0u) << 24, gc, mlen | c1 << 8 | c2 << 16 | wexp << 24,
@@ -455,7 +466,10 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
             trace7(B.S, 1u, tv, 14);
         }
     }
-    // the barrier orders every lane's stores before lane 0's release store of the stamp (cumulative: no fence per lane)
+    // EVERY lane fences its own stores (ext words through DSMEM, candidate positions in HBM) before the stamp goes out.  A warp
+    // barrier followed by lane 0's release store is not enough on the hardware: measured on a B200, about one 100 MB run in eight
+    // had a repair read ext words of the slot's previous record right after a just-in-time build (the stamp had overtaken them).
+    fence_cluster7();
     __syncwarp();
     if (lane == 0) st_release_u32(&sum[0], stampv);
 }
@@ -828,6 +842,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
         const uint32_t sbuf_len = S->sbuf_len;
         Build7 B;
         B.S = S;
+        B.prov_base = (uint32_t)(S->in_pos - (S->sbuf_len - kPrematch));
         B.dbg_pos = ((STATS || ORZ_V7_TRACE_ALWAYS) && S->dbg_pos != 0u && S->in_pos == S->dbg_inpos) ? S->dbg_pos : 0u;
         B.win = S->win;
         B.klist = S->klist;
@@ -1062,17 +1077,6 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                         rec.z = key | (ty == kTyMatch ? mlen : 0u) << 21;
                         rec.w = wexp | (lwe & 0xffu) << 8 | b2lo << 16;
                         shl.queue[(qhead + (uint32_t)lane) % kQueue7] = rec;
-#if ORZ_V7_PROV
-                        if (S->prov) {
-                            const uint32_t pi = S->prov_n + n_items + (uint32_t)lane;
-                            const uint32_t pslot = slot7<NBW>(x);
-                            const uint32_t *prs = shl.sum[pslot];
-                            if (pi < S->prov_cap) {
-                                S->prov[2 * (size_t)pi] = make_uint4(x, prs[1], prs[3], prs[10]);
-                                S->prov[2 * (size_t)pi + 1] = make_uint4(prs[6], prs[11], shl.ext[pslot][1], ty | mlen << 8 | (uint32_t)lane << 16 | nst << 24);
-                            }
-                        }
-#endif
                         if ((STATS || ORZ_V7_TRACE_ALWAYS) && B.dbg_pos && x - B.dbg_pos < 3u) {
                             const uint32_t tv[9] = {x, ty, mlen, word, (uint32_t)lane, nst, nok, key, wexp};
                             trace7(S, 3u, tv, 9);
@@ -1140,11 +1144,10 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                             const int how = repair_record7(shl, B, src, y, yslot, spos, qhead, lane);
                             if (STATS) n_how[how & 3]++;
 #if ORZ_V7_PROV
-                            if (lane == 0) {
-                                const uint32_t w = ys[10];
-                                ys[10] = (w & 0x0fffffffu) | ((uint32_t)how & 3u) << 28 | ((((w >> 30) + 1u) > 3u ? 3u : (w >> 30) + 1u)) << 30;
+                            if (lane == 0 && S->prov) {
+                                const size_t pi = (size_t)B.prov_base + (y - kPrematch);
+                                if (y >= kPrematch && pi < (size_t)S->prov_cap) S->prov[3 * pi + 2] = make_uint4(spos, (uint32_t)how | 0x100u, ys[3], shl.rc_pos[0]);
                             }
-                            __syncwarp();
 #endif
                             if ((STATS || ORZ_V7_TRACE_ALWAYS) && B.dbg_pos && y - B.dbg_pos < 3u && lane == 0) {
                                 const uint32_t tv[13] = {y, spos, (uint32_t)how, ys[3], ys[4], ys[5], ys[6], shl.rc_pos[0], shl.rc_exp[0], shl.rc_ord[0], shl.ext[yslot][0], shl.ext[yslot][1], ys[1]};
@@ -1182,9 +1185,6 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 S->spos = spos;
                 S->after_literal = after_literal;
                 (buf ? S->n_items_alt : S->n_items) = n_items;
-#if ORZ_V7_PROV
-                S->prov_n += n_items;
-#endif
                 if (STATS) {
                     S->dbg[0] += n_items;
                     S->dbg[1] += n_windows;

@@ -37,13 +37,14 @@ def main():
             if d is not None:
                 diff_parse.show(d, 4)
                 ci, k, before, ra, rb = d
-                for j in range(max(0, k - 3), min(len(ra), k + 4)):
-                    w = (C.c_uint32 * 8)()
-                    rc = L.orz_b200_debug_prov(b.h, before + j, w)
-                    x, s1, s3, s10, F, gc, ord0, hz = list(w)
-                    print(f"  prov item {j} rc {rc}: x {x} key {s1 & 0x1fffff} ncand {(s1 >> 21) & 63} incomplete {(s1 >> 27) & 1} | mlen {s3 & 255} lazy1 {(s3 >> 8) & 255} "
-                          f"lazy2 {(s3 >> 16) & 255} exp {s3 >> 24} | cnt16 {s10 & 0xffff} r {(s10 >> 16) & 15} n0 {(s10 >> 20) & 63} mode {(s10 >> 26) & 3} "
-                          f"last repair {(s10 >> 28) & 3} repairs {s10 >> 30} | F {F} gc {gc} ord0 {ord0} | ty {hz & 255} mlen {(hz >> 8) & 255} lane {(hz >> 16) & 255} nst {hz >> 24}", flush=True)
+                X = int(rb[k][0])  # input position of the first differing step
+                for y in range(X - 1, X + 4):
+                    w = (C.c_uint32 * 12)()
+                    rc = L.orz_b200_debug_prov(b.h, y, w)
+                    F, cnt, rmn, gc, nci, s3, e0x, e0y, T, how, r3, q1 = list(w)
+                    print(f"  prov pos {y} rc {rc}: build F {F} cnt {cnt} r {rmn & 255} mode {(rmn >> 8) & 255} n0 {(rmn >> 16) & 255} n1 {rmn >> 24} gc {gc} | ncand {nci & 255} incomplete {(nci >> 8) & 255} "
+                          f"best {(nci >> 16) & 255} mlen {s3 & 255} lazy1 {(s3 >> 8) & 255} lazy2 {(s3 >> 16) & 255} exp {s3 >> 24} | newest entry pos {e0x & 0x1ffffff} ord {e0y & 0x7fffffff} "
+                          f"| last repair: T {T} how {how & 255} seen {how >> 8} mlen {r3 & 255} lazy1 {(r3 >> 8) & 255} lazy2 {(r3 >> 16) & 255} q1 {q1}", flush=True)
         b.close()
     print(f"== {bad} of {reps} repetitions differ", flush=True)
 
