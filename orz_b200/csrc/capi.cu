@@ -380,8 +380,8 @@ static orz_batch *batch_create(int device, int mode, const orz_lzcfg *cfg, int n
             if (i == 0 && v7 && getenv("ORZ_B200_PROV")) { // debugging aid of the A/B builds: provenance of every parse step (stream 0 only)
                 const size_t cap = in_len[i] + 1024;
                 void *p = nullptr;
-                if (cudaMalloc(&p, cap * 48) == cudaSuccess) {
-                    cudaMemset(p, 0, cap * 48);
+                if (cudaMalloc(&p, cap * 64) == cudaSuccess) {
+                    cudaMemset(p, 0, cap * 64);
                     S.prov = reinterpret_cast<uint4 *>(p);
                     S.prov_cap = (uint32_t)cap;
                     b->prov = p;
@@ -529,10 +529,10 @@ extern "C" int orz_batch_run(orz_batch *b) {
                     "orz_b200 stage A v7: steps %llu windows %llu (%.2f steps/window) polls-not-ready %llu repairs %llu (%.4f/step: %llu records re-resolved — %llu alias, %llu one newer node, %llu in full — %llu rebuilt from HBM) "
                     "builds %llu (%.2f/step, %.0f cycles each), refreshes %llu (parse waited for one %llu times); list lag %.1f steps / %.0f bytes; "
                     "resolver cycles/step: total %.1f = team %.1f + chase %.1f + hand-over %.1f + repair %.1f + wait %.1f; verification cuts %llu; rounds ended by: block end / item cap %llu, repair %llu, record not built %llu, edge record %llu; "
-                    "latency probes (cycles): 32 dependent IMADs %.0f, 16 dependent SHFLs %.0f, 16 dependent LDS %.0f\n",
+                    "latency probes (cycles): 32 dependent IMADs %.0f, 16 dependent SHFLs %.0f, 16 dependent LDS %.0f; records seen with their stamp before their words: %llu by the decide team, %llu by repairs\n",
                     d[0], d[1], (double)d[0] / wn, d[2], d[3], d[3] / st, c[6], c[21], c[22], c[23], c[7], d[4], d[4] / st, d[4] ? (double)c[8] / d[4] : 0.0, d[5], d[6], c[9] / wn, c[10] / wn,
                     c[0] / st, c[1] / st, c[2] / st, c[3] / st, c[4] / st, c[5] / st, c[11], c[16] + c[19], c[17], c[18], c[20], c[15] ? (double)c[12] / c[15] : 0.0,
-                    c[15] ? (double)c[13] / c[15] : 0.0, c[15] ? (double)c[14] / c[15] : 0.0);
+                    c[15] ? (double)c[13] / c[15] : 0.0, c[15] ? (double)c[14] / c[15] : 0.0, d[7] & 0xffffull, d[7] >> 16);
         }
         if (b->v7 && getenv("ORZ_B200_DBG_POS")) {
             for (int i = 0; i < b->n; i++) { // the event trace of ORZ_B200_DBG_POS: tag | words << 24, then the words
@@ -604,11 +604,11 @@ extern "C" void *orz_batch_result_dev(orz_batch *b, int i) {
     return b->d_out[i];
 }
 
-// debugging aid (not part of include/orz_b200.h): the three uint4 of provenance that stage A left for input position `index` of stream 0
-extern "C" int orz_b200_debug_prov(orz_batch *b, size_t index, uint32_t *out12) {
-    if (!b || !b->prov || !out12) return ORZ_EARG;
+// debugging aid (not part of include/orz_b200.h): the four uint4 of provenance that stage A left for input position `index` of stream 0
+extern "C" int orz_b200_debug_prov(orz_batch *b, size_t index, uint32_t *out16) {
+    if (!b || !b->prov || !out16) return ORZ_EARG;
     DevGuard g(b->device);
-    return cudaMemcpy(out12, reinterpret_cast<const uint8_t *>(b->prov) + index * 48, 48, cudaMemcpyDeviceToHost) == cudaSuccess ? ORZ_OK : ORZ_ECUDA;
+    return cudaMemcpy(out16, reinterpret_cast<const uint8_t *>(b->prov) + index * 64, 64, cudaMemcpyDeviceToHost) == cudaSuccess ? ORZ_OK : ORZ_ECUDA;
 }
 
 extern "C" int orz_batch_timing(orz_batch *b, int cls, float *total_ms, int *launches) {

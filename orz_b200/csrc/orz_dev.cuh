@@ -175,7 +175,7 @@ struct EncStream {
     uint32_t dbg_pos;
     uint32_t dbgx_n;
     uint32_t dbgx[1024];
-    // provenance of the probe records (A/B builds with ORZ_V7_PROV, ORZ_B200_PROV=1): three uint4 per input position (build, build, last repair)
+    // provenance of the probe records (A/B builds with ORZ_V7_PROV, ORZ_B200_PROV=1): four uint4 per input position (build, build, last repair, what the repair read)
     uint4 *prov;
     uint32_t prov_cap, prov_n;
 };

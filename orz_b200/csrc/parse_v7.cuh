@@ -208,6 +208,7 @@ struct ParseShared7 {
     uint32_t fed_hi;                        // inring holds window bytes [max(fed_lo0, fed_hi - 4096), fed_hi)
     uint32_t fed_lo0;
     uint32_t team_base;                     // first position of the decide team's round (the rounds are paced by named barriers 1 and 2)
+    uint32_t torn;                          // records whose stamp was there before their words were (checksum mismatch; counted, then waited for)
     // refresh of records that went stale well ahead of the parse (bit = record slot): the decide team asks (`req`), the builder that
     // owns the slot rebuilds the record against the present frontier (`busy` while it does)
     uint32_t req[kRing7 / 32];
@@ -269,6 +270,22 @@ __device__ __forceinline__ void fm_round(FmState &st, bool valid, int lcp, uint3
         }
         cur = u;
     }
+}
+
+// Checksums of a probe record (summary words 10 and 11).  The stamp alone is not a safe "record complete" signal on the hardware:
+// on a B200 a reader that saw the new stamp could still read words of the slot's previous record a moment later (one 100 MB run
+// in eight took a wrong decision that way, always right after a just-in-time build).  Word 10 covers summary words 1..9, word 11
+// the ext words a repair reads; both are salted with the position, so a stale checksum of the previous occupant never matches.
+__device__ __forceinline__ uint32_t sumcheck7(uint32_t y, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7, uint32_t w8,
+                                              uint32_t w9) {
+    return (w1 ^ __funnelshift_l(w2, w2, 3) ^ __funnelshift_l(w3, w3, 7) ^ __funnelshift_l(w4, w4, 11) ^ __funnelshift_l(w5, w5, 13) ^ __funnelshift_l(w6, w6, 17) ^
+            __funnelshift_l(w7, w7, 19) ^ __funnelshift_l(w8, w8, 23) ^ __funnelshift_l(w9, w9, 29)) +
+           y * 0x9E3779B1u + 0x5bd1e995u;
+}
+// the ext part: lane l holds candidate words l and 32 + l (0 where the record has none); F_ext and ord0 go in once
+__device__ __forceinline__ uint32_t extcheck7(uint32_t y, uint32_t f_ext, uint32_t ord0, uint32_t c0, uint32_t c1, int lane) {
+    const uint32_t mine = __funnelshift_l(c0, c0, lane & 31) ^ __funnelshift_l(c1, c1, (lane + 7) & 31);
+    return __reduce_xor_sync(kFull, mine) ^ __funnelshift_l(f_ext, f_ext, 5) ^ __funnelshift_l(ord0, ord0, 9) ^ (y * 0x85EBCA6Bu + 0x2545F491u);
 }
 
 // event trace of one position (instrumented build only): see EncStream::dbgx
@@ -432,8 +449,11 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
             __syncwarp();
         }
     }
-    if (ok0) ext[2 + lane] = (uint32_t)lcp0 | kentry_exp(en) << 8 | ((ord0 - kentry_ord(en)) & 0xfffu) << 16;
-    if (ok1 && 32 + lane < kExtCand) ext[2 + 32 + lane] = (uint32_t)lcp1 | kentry_exp(en1) << 8 | ((ord0 - kentry_ord(en1)) & 0xfffu) << 16;
+    const uint32_t xw0 = ok0 ? ((uint32_t)lcp0 | kentry_exp(en) << 8 | ((ord0 - kentry_ord(en)) & 0xfffu) << 16) : 0u;
+    const uint32_t xw1 = (ok1 && 32 + lane < kExtCand) ? ((uint32_t)lcp1 | kentry_exp(en1) << 8 | ((ord0 - kentry_ord(en1)) & 0xfffu) << 16) : 0u;
+    if (ok0) ext[2 + lane] = xw0;
+    if (ok1 && 32 + lane < kExtCand) ext[2 + 32 + lane] = xw1;
+    const uint32_t xcheck = extcheck7(y, F, ord0, xw0, xw1, lane);
     uint32_t *gx = B.gext + (size_t)slot * kExtCand;
     if (ok0) gx[lane] = p0;
     if (ok1 && 32 + lane < kExtCand) gx[32 + lane] = p1;
@@ -451,12 +471,15 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
         sum[7] = hw_lit | wv_lit << 15;
         sum[8] = hw_m | wv_m << 15;
         sum[9] = (uint32_t)(mf < 0 ? 0 : mf) | (uint32_t)(m1m < 0 ? 0 : m1m) << 8 | (uint32_t)(m2m < 0 ? 0 : m2m) << 16;
+        sum[10] = sumcheck7(y, (c << 13 | e0) | (uint32_t)ncand << 21 | (incomplete ? 1u : 0u) << 27, h2 | (cur4 & 0xffffu) << 15, mlen | c1 << 8 | c2 << 16 | wexp << 24, word, ordmin, F,
+                            hw_lit | wv_lit << 15, hw_m | wv_m << 15, (uint32_t)(mf < 0 ? 0 : mf) | (uint32_t)(m1m < 0 ? 0 : m1m) << 8 | (uint32_t)(m2m < 0 ? 0 : m2m) << 16);
+        sum[11] = xcheck;
 #if ORZ_V7_PROV
         if (B.S->prov) { // provenance of the build, by absolute input position (three uint4 per position: build, build, last repair)
             const size_t pi = (size_t)B.prov_base + (y - kPrematch);
             if (y >= kPrematch && pi < (size_t)B.S->prov_cap) {
-                B.S->prov[3 * pi] = make_uint4(F, cnt, r | (uint32_t)mode << 8 | (uint32_t)n0 << 16 | (uint32_t)n1 << 24, gc);
-                B.S->prov[3 * pi + 1] = make_uint4((uint32_t)ncand | (incomplete ? 1u : 0u) << 8 | ((uint32_t)st.best & 0xffu) << 16, mlen | c1 << 8 | c2 << 16 | wexp << 24, en.x, en.y);
+                B.S->prov[4 * pi] = make_uint4(F, cnt, r | (uint32_t)mode << 8 | (uint32_t)n0 << 16 | (uint32_t)n1 << 24, gc);
+                B.S->prov[4 * pi + 1] = make_uint4((uint32_t)ncand | (incomplete ? 1u : 0u) << 8 | ((uint32_t)st.best & 0xffu) << 16, mlen | c1 << 8 | c2 << 16 | wexp << 24, en.x, en.y);
             }
         }
 #endif
@@ -524,10 +547,24 @@ struct ByteSrc7 {
 // Returns 0 if the record has to be rebuilt from HBM instead (incomplete record, log does not reach back to F_ext, > 32 recent steps),
 // else how it was repaired: 1 = nothing to do (the key-hash table aliased), 2 = one newer node took the first place, 3 = re-resolved.
 __device__ __forceinline__ int repair_record7(ParseShared7 &shl, const Build7 &B, const ByteSrc7 &src, uint32_t y, uint32_t slot, uint32_t T,
-                                               uint32_t qhead, int lane) {
+                                               uint32_t qhead, int lane, uint32_t *dbg4 = nullptr) {
     uint32_t *rs = shl.sum[slot];
     const uint32_t *ex = shl.ext[slot];
-    const uint32_t w1 = rs[1];
+    // the record must be whole before anything is derived from it (see sumcheck7): wait for late words, give up after a while
+    uint32_t w1 = 0;
+    for (int tries = 0;; tries++) {
+        w1 = ld_vol_u32(rs + 1);
+        const uint32_t n = (w1 >> 21) & 0x3fu;
+        const uint32_t c0 = (uint32_t)lane < n ? ld_vol_u32(ex + 2 + lane) : 0u;
+        const uint32_t c1 = (32u + (uint32_t)lane < n && 32 + lane < kExtCand) ? ld_vol_u32(ex + 34 + lane) : 0u;
+        const bool ok = sumcheck7(y, w1, ld_vol_u32(rs + 2), ld_vol_u32(rs + 3), ld_vol_u32(rs + 4), ld_vol_u32(rs + 5), ld_vol_u32(rs + 6), ld_vol_u32(rs + 7), ld_vol_u32(rs + 8),
+                                  ld_vol_u32(rs + 9)) == ld_vol_u32(rs + 10) &&
+                        extcheck7(y, ld_vol_u32(ex), ld_vol_u32(ex + 1), c0, c1, lane) == ld_vol_u32(rs + 11);
+        if (__all_sync(kFull, ok)) break;
+        if (tries == 0 && lane == 0) atomicAdd(&shl.torn, 0x10000u);
+        if (tries > 200000) return 0; // (never seen: the record is then rebuilt from HBM)
+        ORZ_POLL();
+    }
     if ((w1 >> 27) & 1u) return 0;
     const uint32_t key = w1 & 0x1fffffu, nold = (w1 >> 21) & 0x3fu, c = key >> 13;
     const uint32_t F_ext = ex[0], ord0 = ex[1];
@@ -554,6 +591,12 @@ __device__ __forceinline__ int repair_record7(ParseShared7 &shl, const Build7 &B
         k += (uint32_t)__popc(hm);
         newer_c += (uint32_t)__popc(cm);
         if (__ballot_sync(kFull, !inrange)) reached = true;
+    }
+    if (dbg4) {
+        dbg4[0] = w1;
+        dbg4[1] = F_ext;
+        dbg4[2] = k | (reached ? 1u : 0u) << 8 | bc << 12;
+        dbg4[3] = 0xffffffffu;
     }
     if (!reached || k > 32u) return 0;
     if (k == 0) { // the key-hash table aliased: nothing decided since F_ext has this key
@@ -634,6 +677,7 @@ __device__ __forceinline__ int repair_record7(ParseShared7 &shl, const Build7 &B
         }
         const unsigned vm = __ballot_sync(kFull, valid);
         const int nv = vm == 0xffffffffu ? 32 : (__ffs(~vm) - 1); // alive candidates form a prefix
+        if (dbg4 && round == 0) dbg4[3] = (uint32_t)nv | (uint32_t)dmax << 8 | nold << 16 | (uint32_t)(__shfl_sync(kFull, lcp, 0) & 0xff) << 24;
         valid = lane < nv;
         m1 = max(m1, warp_max_u((valid && m < B.depth1) ? lcp : -1));
         m2 = max(m2, warp_max_u((valid && m < B.depth2) ? lcp : -1));
@@ -700,9 +744,12 @@ __device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t round_
     // afterwards, so a matching stamp covers every field.
     const uint4 a = lds_volatile_v4(rs);
     const uint4 b = lds_volatile_v4(rs + 4);
-    const uint32_t wmat = ld_vol_u32(rs + 8);
+    const uint4 c4 = lds_volatile_v4(rs + 8); // words update of a match, maxima without the last candidate, the two checksums
+    const uint32_t wmat = c4.x;
     const uint32_t stamp2 = ld_vol_u32(rs); // (a rebuild in place takes the stamp away first and returns it with another generation)
-    const bool ready = (a.x & 0x1ffffffu) == x && a.x == stamp2;
+    const bool sum_ok = sumcheck7(x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c4.x, c4.y) == c4.z;
+    const bool ready = (a.x & 0x1ffffffu) == x && a.x == stamp2 && sum_ok;
+    if ((a.x & 0x1ffffffu) == x && a.x == stamp2 && !sum_ok) atomicAdd(&shl.torn, 1u); // (counted: the stamp was there, the words were not)
     const uint32_t key = a.y & 0x1fffffu, c = key >> 13;
     const bool incomplete = (a.y >> 27) & 1u;
     const uint32_t h2 = a.z & 0x7fffu, b2 = a.z >> 15;
@@ -828,6 +875,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
             shl.qitem = 0;
             shl.done = 0;
             shl.team_base = S->spos;
+            shl.torn = 0;
             // the feeder starts 2048 bytes behind the parse position (16-byte aligned, inside the allocated window)
             uint32_t f0 = (S->spos - 2048u) & ~15u;
             const uint32_t wlo = (S->win_lo + 15u) & ~15u;
@@ -1141,17 +1189,31 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                                     }
                                 }
                             }
+#if ORZ_V7_PROV
+                            uint32_t rdbg[4] = {0, 0, 0, 0};
+                            const int how = repair_record7(shl, B, src, y, yslot, spos, qhead, lane, rdbg);
+#else
                             const int how = repair_record7(shl, B, src, y, yslot, spos, qhead, lane);
+#endif
+                            if (how && lane == 0) ys[10] = sumcheck7(y, ys[1], ys[2], ys[3], ys[4], ys[5], ys[6], ys[7], ys[8], ys[9]); // (the repair rewrote summary words)
+                            __syncwarp();
                             if (STATS) n_how[how & 3]++;
 #if ORZ_V7_PROV
                             if (lane == 0 && S->prov) {
                                 const size_t pi = (size_t)B.prov_base + (y - kPrematch);
-                                if (y >= kPrematch && pi < (size_t)S->prov_cap) S->prov[3 * pi + 2] = make_uint4(spos, (uint32_t)how | 0x100u, ys[3], shl.rc_pos[0]);
+                                if (y >= kPrematch && pi < (size_t)S->prov_cap) {
+                                    const uint32_t *pex = shl.ext[yslot];
+                                    S->prov[4 * pi + 2] = make_uint4(spos, (uint32_t)how | 0x100u | (rmask & 7u) << 12 | k << 16, ys[3], shl.rc_pos[0]);
+                                    S->prov[4 * pi + 3] = make_uint4(rdbg[0], rdbg[1], rdbg[2], rdbg[3]);
+                                    (void)pex;
+                                }
                             }
 #endif
                             if ((STATS || ORZ_V7_TRACE_ALWAYS) && B.dbg_pos && y - B.dbg_pos < 3u && lane == 0) {
-                                const uint32_t tv[13] = {y, spos, (uint32_t)how, ys[3], ys[4], ys[5], ys[6], shl.rc_pos[0], shl.rc_exp[0], shl.rc_ord[0], shl.ext[yslot][0], shl.ext[yslot][1], ys[1]};
-                                trace7(S, 2u, tv, 13);
+                                const uint32_t *ex = shl.ext[yslot];
+                                const uint32_t tv[24] = {y, spos, (uint32_t)how, ys[3], ys[4], ys[5], ys[6], shl.rc_pos[0], shl.rc_exp[0], shl.rc_ord[0], ex[0], ex[1], ys[1],
+                                                         shl.bcnt[(ys[1] >> 13) & 0xffu], yslot, qhead, ex[2], ex[3], ex[4], ex[5], ex[6], ex[7], ex[8], ex[9]};
+                                trace7(S, 2u, tv, 24);
                             }
                             if (!how) {
                                 if (STATS) n_rep_hard++;
@@ -1184,6 +1246,7 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                 }
                 S->spos = spos;
                 S->after_literal = after_literal;
+                if (!wd_code) S->dbg[7] += ld_vol_u32(&shl.torn);
                 (buf ? S->n_items_alt : S->n_items) = n_items;
                 if (STATS) {
                     S->dbg[0] += n_items;

@@ -322,6 +322,7 @@ uint32_t collective(int op, uint32_t mask, uint32_t v, uint32_t param) {
         case OP_MIN: red = first ? x : std::min(red, x); break;
         case OP_ADD: red = first ? x : red + x; break;
         case OP_OR: red = first ? x : (red | x); break;
+        case OP_XOR: red = first ? x : (red ^ x); break;
         case OP_AND: red = first ? x : (red & x); break;
         default: break;
         }

@@ -54,7 +54,7 @@ struct Ctx {
 };
 extern Ctx *cur;
 
-enum Op { OP_SYNC, OP_IDX, OP_BALLOT, OP_MATCH_ANY, OP_MAX, OP_MIN, OP_ADD, OP_OR, OP_AND };
+enum Op { OP_SYNC, OP_IDX, OP_BALLOT, OP_MATCH_ANY, OP_MAX, OP_MIN, OP_ADD, OP_OR, OP_AND, OP_XOR };
 uint32_t collective(int op, uint32_t mask, uint32_t v, uint32_t param);
 extern int cur_site;                // source site of the collective being executed (see the macros at the end of this file)
 void syncthreads();
@@ -128,6 +128,7 @@ static inline int __reduce_max_sync(unsigned mask, int v) { return (int)(simt::c
 static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) { return simt::collective(simt::OP_MIN, mask, v, 0); }
 static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) { return simt::collective(simt::OP_ADD, mask, v, 0); }
 static inline unsigned __reduce_or_sync(unsigned mask, unsigned v) { return simt::collective(simt::OP_OR, mask, v, 0); }
+static inline unsigned __reduce_xor_sync(unsigned mask, unsigned v) { return simt::collective(simt::OP_XOR, mask, v, 0); }
 static inline unsigned __reduce_and_sync(unsigned mask, unsigned v) { return simt::collective(simt::OP_AND, mask, v, 0); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { simt::collective(simt::OP_SYNC, mask, 0, 0); }
 static inline void __syncthreads() { simt::syncthreads(); }

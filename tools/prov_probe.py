@@ -39,12 +39,13 @@ def main():
                 ci, k, before, ra, rb = d
                 X = int(rb[k][0])  # input position of the first differing step
                 for y in range(X - 1, X + 4):
-                    w = (C.c_uint32 * 12)()
+                    w = (C.c_uint32 * 16)()
                     rc = L.orz_b200_debug_prov(b.h, y, w)
-                    F, cnt, rmn, gc, nci, s3, e0x, e0y, T, how, r3, q1 = list(w)
+                    F, cnt, rmn, gc, nci, s3, e0x, e0y, T, how, r3, q1, x1, x2, bcr, s1 = list(w)
                     print(f"  prov pos {y} rc {rc}: build F {F} cnt {cnt} r {rmn & 255} mode {(rmn >> 8) & 255} n0 {(rmn >> 16) & 255} n1 {rmn >> 24} gc {gc} | ncand {nci & 255} incomplete {(nci >> 8) & 255} "
                           f"best {(nci >> 16) & 255} mlen {s3 & 255} lazy1 {(s3 >> 8) & 255} lazy2 {(s3 >> 16) & 255} exp {s3 >> 24} | newest entry pos {e0x & 0x1ffffff} ord {e0y & 0x7fffffff} "
-                          f"| last repair: T {T} how {how & 255} seen {how >> 8} mlen {r3 & 255} lazy1 {(r3 >> 8) & 255} lazy2 {(r3 >> 16) & 255} q1 {q1}", flush=True)
+                          f"| last repair: T {T} how {how & 255} seen {(how >> 8) & 1} rmask {(how >> 12) & 7} nbr {how >> 16} mlen {r3 & 255} lazy1 {(r3 >> 8) & 255} lazy2 {(r3 >> 16) & 255} q1 {q1} "
+                          f"| the repair used: key {x1 & 0x1fffff} ncand {(x1 >> 21) & 63} F_ext {x2} k {bcr & 255} reached {(bcr >> 8) & 1} bc {bcr >> 12} nv0 {s1 & 255} dmax {(s1 >> 8) & 255} nold {(s1 >> 16) & 255} lcp0 {s1 >> 24}", flush=True)
         b.close()
     print(f"== {bad} of {reps} repetitions differ", flush=True)
 

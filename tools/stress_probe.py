@@ -30,7 +30,7 @@ def main():
             fd = next((i for i in range(fd, min(fd + 4096, m)) if got[i] != want[i]), fd)
             bad.append({"rep": rep, "len": len(got), "first_diff": fd})
             out = os.path.join(ROOT, "gpurun_out", f"bad_stream_{len(got)}_{fd}.bin")
-            if len(bad) <= 2 and not os.path.exists(out):  # (keep the merge-back small: two samples)
+            if len(bad) <= 1 and not os.path.exists(out):  # (keep the merge-back small: one sample)
                 os.makedirs(os.path.dirname(out), exist_ok=True)
                 open(out, "wb").write(got)
     print(json.dumps({"bytes": n, "level": level, "reps": reps, "want_len": len(want), "mismatches": bad}), flush=True)

@@ -28,7 +28,7 @@ def main():
         sys.stderr.flush()
         if got != want:
             out = os.path.join(ROOT, "gpurun_out", f"bad_stream_rep{rep}_{len(got)}.bin")
-            if sum(f.startswith("bad_stream_rep") for f in os.listdir(os.path.join(ROOT, "gpurun_out"))) < 3:
+            if os.environ.get("ORZ_TRACE_SAVE") and sum(f.startswith("bad_stream_rep") for f in os.listdir(os.path.join(ROOT, "gpurun_out"))) < 1:
                 open(out, "wb").write(got)
         print(f"== rep {rep} identical {got == want} len {len(got)} want {len(want)}", file=sys.stderr, flush=True)
 
