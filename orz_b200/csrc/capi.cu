@@ -534,6 +534,11 @@ extern "C" int orz_batch_run(orz_batch *b) {
                     c[0] / st, c[1] / st, c[2] / st, c[3] / st, c[4] / st, c[5] / st, c[11], c[16] + c[19], c[17], c[18], c[20], c[15] ? (double)c[12] / c[15] : 0.0,
                     c[15] ? (double)c[13] / c[15] : 0.0, c[15] ? (double)c[14] / c[15] : 0.0, d[7] & 0xffffull, d[7] >> 16);
         }
+        if (b->v7 && getenv("ORZ_B200_TORN")) { // records seen with their stamp before their words (stage A v7 waits for them; see sumcheck7)
+            unsigned long long t = 0;
+            for (int i = 0; i < b->n; i++) t += tmp[i].dbg[7];
+            fprintf(stderr, "orz_b200 stage A v7: incomplete records seen: %llu by the decide team, %llu by repairs\n", t & 0xffffull, t >> 16);
+        }
         if (b->v7 && getenv("ORZ_B200_DBG_POS")) {
             for (int i = 0; i < b->n; i++) { // the event trace of ORZ_B200_DBG_POS: tag | words << 24, then the words
                 const uint32_t nx = tmp[i].dbgx_n < 1024u ? tmp[i].dbgx_n : 1024u;

@@ -59,7 +59,7 @@ constexpr int kListCap = 64;           // entries per key list (circular, newest
 constexpr int kMaxDepth7 = 48;         // deepest LZCfg depth this kernel handles (levels 0-2 use 45)
 constexpr int kRing7 = 480;            // probe record slots in CTA 0's shared memory (112 builders x 4, 240 x 2, 6 x 80)
 #ifndef ORZ_V7_LEAD
-#define ORZ_V7_LEAD 96
+#define ORZ_V7_LEAD 160 // (measured on 6 MB / 100 MB of enwik8 -l2: 96: 11.7 / 12.2 MB/s, 128: 12.3, 160: 12.6 / 13.3, 224: 12.4)
 #endif
 #ifndef ORZ_V7_MUT_TIGHT
 #define ORZ_V7_MUT_TIGHT 0u // (mutation hook of the A/B builds: a wrong ring-edge check must break the 100 MB identity test)

@@ -52,6 +52,18 @@ def test_config1_enwik8_prefix_other_levels(enwik8, level):
     assert (len(got), _sha(got)) == (len(want), _sha(want))
 
 
+def test_repeated_encodes_are_identical(enwik8):
+    """Stage A's builders, decide team and resolver run concurrently; a protocol hole shows up as a stream that differs from the
+    oracle's in a few runs out of a hundred (round 2: a repair used a probe record before all of its words had arrived — records
+    now carry checksums).  17 MB of enwik8 (one block slide, the stretch that failed most often) encoded eight times, every
+    stream compared."""
+    data = enwik8[:17_000_000]
+    want = pyoracle.encode(data, 2)
+    for rep in range(8):
+        got = orz_b200.encode(data, 2)
+        assert (len(got), _sha(got)) == (len(want), _sha(want)), f"repetition {rep} differs from the oracle's stream"
+
+
 def test_config0_roundtrip_l0(enwik8):
     """configs[0] is the reference's CPU case (encode -l0, decode, cmp); here the GPU decodes the oracle's -l0 stream of 40 MB."""
     data = enwik8[:40_000_000]
