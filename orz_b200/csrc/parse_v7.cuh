@@ -76,6 +76,13 @@ constexpr int kRing7 = 480;            // probe record slots in CTA 0's shared m
 #ifndef ORZ_V7_TRACE_ALWAYS
 #define ORZ_V7_TRACE_ALWAYS 0 // 1: the event trace of ORZ_B200_DBG_POS is compiled into the production instantiation too (A/B builds only)
 #endif
+#ifndef ORZ_V7_TEST_TEAR
+#define ORZ_V7_TEST_TEAR 0 // (fault injection of the emulator tests: builders publish the stamp BEFORE the words of a record, the way the
+                           // hardware was seen to; readers must find out through the checksums and wait)
+#endif
+#ifndef ORZ_V7_MUT_NOCHECK
+#define ORZ_V7_MUT_NOCHECK 0 // (mutation hook: readers ignore the record checksums — with the fault injection on, the stream must then differ)
+#endif
 #ifndef ORZ_V7_PROV
 #define ORZ_V7_PROV 0 // 1: every handed-over step leaves two uint4 of provenance (how its record came about) in EncStream::prov (A/B builds only)
 #endif
@@ -449,6 +456,15 @@ __device__ __forceinline__ void build_record7(const Build7 &B, uint32_t y, uint3
             __syncwarp();
         }
     }
+#if ORZ_V7_TEST_TEAR
+    if (mode == 0) { // the stamp first, then a pause in which the decide team and the resolver get to see the slot's old words under it
+        if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&sum[0]) = stampv;
+        for (int i = 0; i < 6; i++) {
+            __syncwarp();
+            ORZ_POLL();
+        }
+    }
+#endif
     const uint32_t xw0 = ok0 ? ((uint32_t)lcp0 | kentry_exp(en) << 8 | ((ord0 - kentry_ord(en)) & 0xfffu) << 16) : 0u;
     const uint32_t xw1 = (ok1 && 32 + lane < kExtCand) ? ((uint32_t)lcp1 | kentry_exp(en1) << 8 | ((ord0 - kentry_ord(en1)) & 0xfffu) << 16) : 0u;
     if (ok0) ext[2 + lane] = xw0;
@@ -557,7 +573,7 @@ __device__ __forceinline__ int repair_record7(ParseShared7 &shl, const Build7 &B
         const uint32_t n = (w1 >> 21) & 0x3fu;
         const uint32_t c0 = (uint32_t)lane < n ? ld_vol_u32(ex + 2 + lane) : 0u;
         const uint32_t c1 = (32u + (uint32_t)lane < n && 32 + lane < kExtCand) ? ld_vol_u32(ex + 34 + lane) : 0u;
-        const bool ok = sumcheck7(y, w1, ld_vol_u32(rs + 2), ld_vol_u32(rs + 3), ld_vol_u32(rs + 4), ld_vol_u32(rs + 5), ld_vol_u32(rs + 6), ld_vol_u32(rs + 7), ld_vol_u32(rs + 8),
+        const bool ok = ORZ_V7_MUT_NOCHECK || sumcheck7(y, w1, ld_vol_u32(rs + 2), ld_vol_u32(rs + 3), ld_vol_u32(rs + 4), ld_vol_u32(rs + 5), ld_vol_u32(rs + 6), ld_vol_u32(rs + 7), ld_vol_u32(rs + 8),
                                   ld_vol_u32(rs + 9)) == ld_vol_u32(rs + 10) &&
                         extcheck7(y, ld_vol_u32(ex), ld_vol_u32(ex + 1), c0, c1, lane) == ld_vol_u32(rs + 11);
         if (__all_sync(kFull, ok)) break;
@@ -747,7 +763,7 @@ __device__ __forceinline__ void decide_block7(ParseShared7 &shl, uint32_t round_
     const uint4 c4 = lds_volatile_v4(rs + 8); // words update of a match, maxima without the last candidate, the two checksums
     const uint32_t wmat = c4.x;
     const uint32_t stamp2 = ld_vol_u32(rs); // (a rebuild in place takes the stamp away first and returns it with another generation)
-    const bool sum_ok = sumcheck7(x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c4.x, c4.y) == c4.z;
+    const bool sum_ok = ORZ_V7_MUT_NOCHECK || sumcheck7(x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c4.x, c4.y) == c4.z;
     const bool ready = (a.x & 0x1ffffffu) == x && a.x == stamp2 && sum_ok;
     if ((a.x & 0x1ffffffu) == x && a.x == stamp2 && !sum_ok) atomicAdd(&shl.torn, 1u); // (counted: the stamp was there, the words were not)
     const uint32_t key = a.y & 0x1fffffu, c = key >> 13;

@@ -77,6 +77,32 @@ def test_emulated_kernels_under_random_interleavings(emu, seed):
     assert got == [_want(_data(case), 2)]
 
 
+def test_readers_wait_for_records_whose_stamp_came_first():
+    """Fault injection (tests/simt/Makefile: -DORZ_V7_TEST_TEAR=1): every builder publishes the stamp of a record BEFORE its words and
+    pauses in between — on the B200 a reader was seen to find the stamp of a new record over words of the slot's previous one
+    (DESIGN.md 1a-iv).  The decide team and the repairs must notice through the record checksums, wait, and still produce the
+    oracle's stream; the library's counters must show that they did notice."""
+    lib = os.path.join(SIMT, "liborz_b200_emu_tear.so")
+    subprocess.check_call(["make", "-C", SIMT, "liborz_b200_emu_tear.so"], stdout=subprocess.DEVNULL)
+    case = {"gen": "text_like", "n": 30000, "seed": 31}
+    env = dict(os.environ, ORZ_B200_LIB=lib, ORZ_B200_TEST_EMULATOR="1", SIMT_SWITCH_LIMIT="20000000000", ORZ_B200_V7_CLUSTER="1",
+               ORZ_B200_TORN="1", SIMT_SEED="3")
+    out = subprocess.run([sys.executable, os.path.join(SIMT, "run_case.py"), json.dumps({"level": 2, "cases": [case]})], env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert json.loads(out.stdout.strip().splitlines()[-1]) == [_want(_data(case), 2)]
+    seen = [ln for ln in out.stderr.splitlines() if "incomplete records seen" in ln]
+    assert seen, out.stderr[-500:]
+    team, repairs = (int(x) for x in __import__("re").findall(r"(\d+) by", seen[-1]))
+    assert team + repairs > 0, seen[-1]
+    # the mutation: the same fault with the readers' checks off must break the stream, or this test proves nothing
+    lib2 = os.path.join(SIMT, "liborz_b200_emu_tear_nocheck.so")
+    subprocess.check_call(["make", "-C", SIMT, "liborz_b200_emu_tear_nocheck.so"], stdout=subprocess.DEVNULL)
+    out2 = subprocess.run([sys.executable, os.path.join(SIMT, "run_case.py"), json.dumps({"level": 2, "cases": [case]})],
+                          env=dict(env, ORZ_B200_LIB=lib2), capture_output=True, text=True, timeout=900)
+    assert out2.returncode != 0 or json.loads(out2.stdout.strip().splitlines()[-1]) != [_want(_data(case), 2)]
+
+
 def test_emulated_legacy_v3_variants(emu):
     """v3 (single-thread executor, per-bucket seqlocks; ring-record layout) is the many-stream kernel; pin it for one stream too."""
     case = {"gen": "text_like", "n": 20000, "seed": 31}
