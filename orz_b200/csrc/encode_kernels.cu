@@ -1461,7 +1461,7 @@ static void launch_parse7_variant(EncStream *d_streams, int n, int buf, cudaStre
 
 // Library configuration, read once per process:
 //   ORZ_B200_STATS=1            stage A v7 runs its instrumented instantiation (counters + clock64 phases, printed by capi.cu)
-//   ORZ_B200_V7_CLUSTER=1|8|16  CTAs per stream of stage A v7 (default 8)
+//   ORZ_B200_V7_CLUSTER=1|8     CTAs per stream of stage A v7 (default 8; 1 = builders beside the resolver, the emulator tests' configuration)
 //   ORZ_B200_LEGACY_STAGE_A=1|v3|v3s|v4   ring-record layout instead of key lists (capi.cu reads it when a batch is created);
 //                               v3 / v3s / v4 additionally pin the kernel (tests)
 struct LibCfg {
@@ -1492,12 +1492,10 @@ void launch_parse(EncStream *d_streams, int n, bool v7, int buf, cudaStream_t st
     const LibCfg &c = lib_cfg();
     if (v7) {
         if (c.stats) {
-            if (c.cluster == 16) launch_parse7_variant<16, 16, true>(d_streams, n, buf, st);
-            else if (c.cluster == 1) launch_parse7_variant<16, 1, true>(d_streams, n, buf, st);
+            if (c.cluster == 1) launch_parse7_variant<16, 1, true>(d_streams, n, buf, st);
             else launch_parse7_variant<16, 8, true>(d_streams, n, buf, st);
         } else {
-            if (c.cluster == 16) launch_parse7_variant<16, 16, false>(d_streams, n, buf, st);
-            else if (c.cluster == 1) launch_parse7_variant<16, 1, false>(d_streams, n, buf, st);
+            if (c.cluster == 1) launch_parse7_variant<16, 1, false>(d_streams, n, buf, st);
             else launch_parse7_variant<16, 8, false>(d_streams, n, buf, st);
         }
         return;

@@ -11,10 +11,9 @@ log=${3:-/tmp/orz_soak.log}
 export ORZ_B200_TEST_EMULATOR=1 SIMT_SWITCH_LIMIT=6000000000000
 size=$(stat -c %s "$corpus")
 seed=$((1000 + worker * 100000))
-configs=("ORZ_B200_PARSE=4" "ORZ_B200_PARSE=4 ORZ_B200_PARSE_WARPS=32" "ORZ_B200_PARSE=5 ORZ_B200_PARSE_WARPS=16"
-         "ORZ_B200_PARSE=5 ORZ_B200_PARSE_CLUSTER=2" "ORZ_B200_PARSE=6 ORZ_B200_PARSE_GROUP=8 ORZ_B200_PARSE_WARPS=16"
-         "ORZ_B200_PARSE=6 ORZ_B200_PARSE_GROUP=8 ORZ_B200_PARSE_WARPS=32" "ORZ_B200_PARSE=6 ORZ_B200_PARSE_GROUP=4 ORZ_B200_PARSE_WARPS=16"
-         "ORZ_B200_PARSE=6 ORZ_B200_PARSE_GROUP=16 ORZ_B200_PARSE_WARPS=32" "ORZ_B200_PARSE=3")
+# (the library reads its switches once per process: one emu_cli run per configuration)
+configs=("ORZ_B200_V7_CLUSTER=1" "ORZ_B200_V7_CLUSTER=8" "ORZ_B200_V7_CLUSTER=1 ORZ_B200_STATS=1" "ORZ_B200_LEGACY_STAGE_A=v4" "ORZ_B200_LEGACY_STAGE_A=v3"
+         "ORZ_B200_LEGACY_STAGE_A=v3s")
 i=0
 while true; do
   cfg=${configs[$(( (i + worker) % ${#configs[@]} ))]}

@@ -1,6 +1,6 @@
 """GPU probe of stage A v7: encodes slices of the bench corpus as one stream, checks the stream against the oracle's,
 prints CUDA-event time per kernel class.  `python tools/v7_probe.py NBYTES [LEVEL] [KEY=VALUE ...]` (library switches
-such as ORZ_B200_STATS=1, ORZ_B200_V7_CLUSTER=16, ORZ_B200_LEGACY_STAGE_A=1 go into the environment BEFORE the library
+such as ORZ_B200_STATS=1, ORZ_B200_LEGACY_STAGE_A=1 go into the environment BEFORE the library
 loads).  Development tool, not a bench line."""
 import hashlib
 import json
