@@ -347,3 +347,22 @@ def test_reference_golden_vectors_when_present():
         assert hashlib.sha256(data).hexdigest() == rec["sha256_in"]
         enc = pyoracle.encode(data, int(rec["level"]))
         assert (len(enc), hashlib.sha256(enc).hexdigest()) == (rec["len"], rec["sha256"]), f
+
+
+def test_parse_diff_tool_locates_the_first_differing_step():
+    """tools/diff_parse.py (the oracle's chunk decoder with its item trace on) is how a stage A timing hole was localised in round 2:
+    two streams of the same input are decoded side by side and the first parse step that differs is reported with its input
+    position.  Here: the -l1 and -l2 streams of one text (same literals / matches until the deeper search finds a longer match)."""
+    from tools import diff_parse
+    data = datagen.text_like(200_000, seed=5)
+    a, b = pyoracle.encode(data, 2), pyoracle.encode(data, 1)
+    assert diff_parse.first_difference(a, a) is None
+    d = diff_parse.first_difference(a, b)
+    assert d is not None
+    ci, k, before, ra, rb = d
+    assert ci == 0 and before == 0 and 0 < k < min(len(ra), len(rb))
+    assert (ra[:k] == rb[:k]).all() and (ra[k] != rb[k]).any()
+    assert int(ra[k][0]) == int(rb[k][0])  # both parses stand at the same input position when they part
+    # every traced position is where the previous item ended: literal +1, WORD +2, match +length
+    adv = np.where(ra[:, 1] < 256, 1, np.where(ra[:, 2] > 0, ra[:, 2], 2))
+    assert (ra[1:, 0] == ra[:-1, 0] + adv[:-1]).all() and int(ra[-1, 0] + adv[-1]) == len(data)
