@@ -573,9 +573,11 @@ __device__ __forceinline__ int repair_record7(ParseShared7 &shl, const Build7 &B
         const uint32_t n = (w1 >> 21) & 0x3fu;
         const uint32_t c0 = (uint32_t)lane < n ? ld_vol_u32(ex + 2 + lane) : 0u;
         const uint32_t c1 = (32u + (uint32_t)lane < n && 32 + lane < kExtCand) ? ld_vol_u32(ex + 34 + lane) : 0u;
-        const bool ok = ORZ_V7_MUT_NOCHECK || sumcheck7(y, w1, ld_vol_u32(rs + 2), ld_vol_u32(rs + 3), ld_vol_u32(rs + 4), ld_vol_u32(rs + 5), ld_vol_u32(rs + 6), ld_vol_u32(rs + 7), ld_vol_u32(rs + 8),
-                                  ld_vol_u32(rs + 9)) == ld_vol_u32(rs + 10) &&
-                        extcheck7(y, ld_vol_u32(ex), ld_vol_u32(ex + 1), c0, c1, lane) == ld_vol_u32(rs + 11);
+        // (the ext checksum holds a warp collective: every lane computes it, whatever its own view of the summary words says)
+        const uint32_t xc = extcheck7(y, ld_vol_u32(ex), ld_vol_u32(ex + 1), c0, c1, lane);
+        const uint32_t sc = sumcheck7(y, w1, ld_vol_u32(rs + 2), ld_vol_u32(rs + 3), ld_vol_u32(rs + 4), ld_vol_u32(rs + 5), ld_vol_u32(rs + 6), ld_vol_u32(rs + 7), ld_vol_u32(rs + 8),
+                                      ld_vol_u32(rs + 9));
+        const bool ok = ORZ_V7_MUT_NOCHECK || (sc == ld_vol_u32(rs + 10) && xc == ld_vol_u32(rs + 11));
         if (__all_sync(kFull, ok)) break;
         if (tries == 0 && lane == 0) atomicAdd(&shl.torn, 0x10000u);
         if (tries > 200000) return 0; // (never seen: the record is then rebuilt from HBM)

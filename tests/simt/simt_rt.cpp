@@ -290,7 +290,8 @@ uint32_t collective(int op, uint32_t mask, uint32_t v, uint32_t param) {
         w->site = site;
     } else if (w->site != site) {
         fail("SIMT emulator: lanes of one warp reached a collective at different source sites (divergent branch around a "
-             "__shfl/__ballot/__syncwarp: undefined behaviour on the GPU)");
+             "__shfl/__ballot/__syncwarp: undefined behaviour on the GPU): source lines " + std::to_string(w->site / 4096) + " and " +
+             std::to_string(site / 4096) + " (0 = a __reduce_*_sync, which carries no site)");
         switch_to(&g_main);
     } else if (w->mask != mask || w->op != op) {
         fail("SIMT emulator: lanes of one warp are in different collectives (divergent __shfl/__ballot masks)");

@@ -339,12 +339,12 @@ static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess
 // `__shfl_sync` at different places of a divergent branch is undefined behaviour (in practice a hang).  The fibre model
 // would happily pair them up, so every textual use of a collective gets a site number (__COUNTER__) and the runtime
 // fails the launch if the lanes of one collective disagree about it.
-#define __shfl_sync(...) (simt::cur_site = __COUNTER__ + 1, __shfl_sync(__VA_ARGS__))
-#define __shfl_up_sync(...) (simt::cur_site = __COUNTER__ + 1, __shfl_up_sync(__VA_ARGS__))
-#define __shfl_down_sync(...) (simt::cur_site = __COUNTER__ + 1, __shfl_down_sync(__VA_ARGS__))
-#define __shfl_xor_sync(...) (simt::cur_site = __COUNTER__ + 1, __shfl_xor_sync(__VA_ARGS__))
-#define __ballot_sync(...) (simt::cur_site = __COUNTER__ + 1, __ballot_sync(__VA_ARGS__))
-#define __any_sync(...) (simt::cur_site = __COUNTER__ + 1, __any_sync(__VA_ARGS__))
-#define __all_sync(...) (simt::cur_site = __COUNTER__ + 1, __all_sync(__VA_ARGS__))
-#define __match_any_sync(...) (simt::cur_site = __COUNTER__ + 1, __match_any_sync(__VA_ARGS__))
-#define __syncwarp(...) (simt::cur_site = __COUNTER__ + 1, __syncwarp(__VA_ARGS__))
+#define __shfl_sync(...) (simt::cur_site = (__LINE__ * 4096 + (__COUNTER__ & 4095) + 1), __shfl_sync(__VA_ARGS__))
+#define __shfl_up_sync(...) (simt::cur_site = (__LINE__ * 4096 + (__COUNTER__ & 4095) + 1), __shfl_up_sync(__VA_ARGS__))
+#define __shfl_down_sync(...) (simt::cur_site = (__LINE__ * 4096 + (__COUNTER__ & 4095) + 1), __shfl_down_sync(__VA_ARGS__))
+#define __shfl_xor_sync(...) (simt::cur_site = (__LINE__ * 4096 + (__COUNTER__ & 4095) + 1), __shfl_xor_sync(__VA_ARGS__))
+#define __ballot_sync(...) (simt::cur_site = (__LINE__ * 4096 + (__COUNTER__ & 4095) + 1), __ballot_sync(__VA_ARGS__))
+#define __any_sync(...) (simt::cur_site = (__LINE__ * 4096 + (__COUNTER__ & 4095) + 1), __any_sync(__VA_ARGS__))
+#define __all_sync(...) (simt::cur_site = (__LINE__ * 4096 + (__COUNTER__ & 4095) + 1), __all_sync(__VA_ARGS__))
+#define __match_any_sync(...) (simt::cur_site = (__LINE__ * 4096 + (__COUNTER__ & 4095) + 1), __match_any_sync(__VA_ARGS__))
+#define __syncwarp(...) (simt::cur_site = (__LINE__ * 4096 + (__COUNTER__ & 4095) + 1), __syncwarp(__VA_ARGS__))
