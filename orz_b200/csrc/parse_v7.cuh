@@ -1467,8 +1467,12 @@ __global__ void __launch_bounds__(NW * 32) orz_parse7_kernel(EncStream *streams,
                     if (!(same_ctx & ~lt_mask & ~(1u << lane))) shl.cnt[ctx] = cbase + (uint32_t)__popc(same_ctx); // group's last lane
                     // ---- ring bytes
                     if (bump && !bump_dead) lmarr[c * kNodesStride + mslot] = (uint8_t)new_lm;
-                    if (!ins_dead) lmarr[c * kNodesStride + slot] = 0;
                 }
+                // An earlier step may bump the node whose ring slot a later step of the batch re-uses (a match 4087 inserts back, found by
+                // the randomized emulator soak): the new node's lenmin 0 must land after that bump (matcher.rs:66-77 in step order).
+                // Two stores from different lanes are ordered by the barrier, not by the warp happening to run in lock step.
+                __syncwarp();
+                if (act && !ins_dead) lmarr[c * kNodesStride + slot] = 0;
                 __threadfence(); // the next batch's lenmin loads (other lanes, L2) must see these stores
                 __syncwarp();
                 tail += n;
